@@ -1,0 +1,133 @@
+// pn2_common.cuh -- shared declarations of libpn2gpu.so (sm_100a).  See include/pn2gpu.h for the C-ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <stdlib.h>
+#include <vector>
+#include <string>
+#include "../../include/pn2gpu.h"
+
+#define NM PN2_NMULTI
+#define PN2_IMG_SHIFT 26                       // src entry = cell | image << 26
+#define PN2_CELL_MASK ((1u << PN2_IMG_SHIFT) - 1u)
+
+void pn2_set_error(const char *fmt, ...);
+
+#define CUDA_TRY(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t e_ = (expr);                                                             \
+        if (e_ != cudaSuccess) {                                                             \
+            pn2_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e_)); \
+            return PN2_ERR_CUDA;                                                             \
+        }                                                                                    \
+    } while (0)
+#define PN2_TRY(expr)                                                                        \
+    do {                                                                                     \
+        int s_ = (expr);                                                                     \
+        if (s_ != PN2_OK) return s_;                                                         \
+    } while (0)
+#define KERNEL_CHECK() CUDA_TRY(cudaGetLastError())
+
+// grow-only device buffer: the tree and the lists are rebuilt every step (src/fmm.c:216-217,1080-1083),
+// the pools are not
+template <typename T>
+struct DBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t n, bool keep = false, cudaStream_t st = 0) {
+        if (n <= cap) return PN2_OK;
+        size_t ncap = n + n / 8 + 64;
+        T *q = nullptr;
+        cudaError_t e = cudaMalloc(&q, ncap * sizeof(T));
+        if (e != cudaSuccess) {
+            pn2_set_error("cudaMalloc(%zu bytes): %s", ncap * sizeof(T), cudaGetErrorString(e));
+            return PN2_ERR_NOMEM;
+        }
+        if (keep && p && cap) cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, st);
+        if (p) { cudaStreamSynchronize(st); cudaFree(p); }
+        p = q; cap = ncap;
+        return PN2_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// packed descriptor of a leaf as a P2P source / sink: 32 bytes, one sector
+struct __align__(32) LeafDesc {
+    double c[3];       // box centre (displaced for LET leaves)
+    int first;         // first particle in the particle array of its set
+    int npart;
+};
+
+// a set of source leaves: local leaves, or the leaves of a received LET
+struct SourceSet {
+    const LeafDesc *desc;     // indexed by cell id (local) / flattened node id (LET)
+    const float4 *rel;        // FP32 mode: (pos - leaf centre) / (2 rs), w = 1
+    const double *pos;        // FP64 mode: absolute positions, double[n][3]
+};
+
+struct P2PConst {
+    double inv2rs;            // 1 / (2 rs): FP32 positions are stored in units of 2 rs
+    double rs, soft, mass;
+    double shift[27][3];      // image displacements; index 0 = none, 1..26 = order of src/fmm.c:1028-1037
+    float q[12];              // g(u) = exp(-u^2) * sum q[k] u^k   (weighted minimax fit)
+    float inv_eps;            // 2 rs / soft
+    int longshort;
+};
+
+// CSR interaction list by sink
+struct CsrList {
+    long nseg;
+    const int *seg_sink;      // sink cell id
+    const long *seg_off;      // [nseg + 1]
+    const unsigned *src;      // source cell | image << 26
+};
+
+struct pn2_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    pn2_params prm{};
+    P2PConst pc{};
+    long launches = 0;
+
+    // ---- particles (tree order) ----
+    int n = 0;
+    DBuf<double> pos;          // [n][3]
+    DBuf<double> acc;          // [n][3]
+    DBuf<float4> rel;          // [n]
+    // ---- cells: leaves 0..nleaf-1, nodes nleaf..nleaf+nnode-1 ----
+    int nleaf = 0, nnode = 0, ncell = 0, nlevel = 0;
+    int first_leaf = 0, last_leaf = 0, first_node = 0, last_node = 0;   // Mode A id space
+    DBuf<double> geom;         // [ncell][6] centre, width
+    DBuf<int> son;             // [ncell][2]
+    DBuf<LeafDesc> desc;       // [ncell] (first, npart valid for nodes too)
+    DBuf<double> M, L;         // [ncell][20]
+    DBuf<int> level_nodes;     // node cell ids grouped by depth
+    std::vector<int> level_off;   // [nlevel + 1]
+    // ---- received LET (Mode A) ----
+    int r_nnode = 0, r_nbody = 0;
+    DBuf<LeafDesc> r_desc;
+    DBuf<double> r_geom, r_M, r_pos;
+    DBuf<float4> r_rel;
+    // ---- scratch ----
+    DBuf<int> ia, ib, ic, id_;
+    DBuf<long> la;
+    DBuf<unsigned> ua, ub;
+    DBuf<unsigned char> tmp;
+    DBuf<unsigned long long> counters;   // [8]
+    double timings[8] = {0};
+    bool have_particles = false, have_tree = false, have_remote = false;
+};
+
+// ---- kernels / launchers implemented across the .cu files ----
+int pn2_launch_p2p(pn2_ctx *h, const CsrList &list, const SourceSet &src, bool src_is_local);
+int pn2_launch_m2l(pn2_ctx *h, const CsrList &list, const double *src_geom, const double *src_M);
+int pn2_launch_p2m(pn2_ctx *h);
+int pn2_launch_m2m(pn2_ctx *h);
+int pn2_launch_l2l_l2p(pn2_ctx *h);
+int pn2_launch_relpos(pn2_ctx *h, const double *pos, const LeafDesc *desc, int ncell_leaf, float4 *rel, int n);
+int pn2_build_csr(pn2_ctx *h, const int *h_s, const int *h_t, long n, int remote_src, int sinks_may_be_nodes, CsrList *out);
+void pn2_modeb_release(pn2_ctx *h);
+void pn2_init_consts(pn2_ctx *h);

@@ -8,6 +8,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+PKG = os.path.join(ROOT, "photons-2.0_b200")
+if PKG not in sys.path:
+    sys.path.insert(0, PKG)
 
 
 def pytest_configure(config):
@@ -41,3 +44,15 @@ def oracle():
     from oracle import pn_oracle
     pn_oracle.lib()
     return pn_oracle
+
+
+@pytest.fixture(scope="session")
+def pn2():
+    """The product's host binding (photons-2.0_b200/pn2gpu.py over libpn2gpu.so)."""
+    import pn2gpu
+    return pn2gpu
+
+
+def image_shifts(box):
+    """The 26 periodic displacements in the reference's order (src/fmm.c:1028-1037)."""
+    return [((q // 9 - 1) * box, ((q // 3) % 3 - 1) * box, (q % 3 - 1) * box) for q in range(27) if q != 13]

@@ -1,0 +1,178 @@
+"""Mode A parity on the GPU (through the C-ABI): the reference's own tree and interaction lists (from the
+oracle, which is pinned bit-exactly to the reference's in test_oracle_golden.py) are handed to the device
+batch by batch, exactly where task_compute_p2p / task_compute_m2l / *_ext sit in src/fmm.c, src/remotes.c.
+
+Tolerances (BASELINE.json north_star): rms relative error <= 1e-6 in FP64 mode, <= 1e-4 in FP32 mode.
+"""
+import numpy as np
+import pytest
+
+from conftest import image_shifts, load_golden, rms_rel
+
+pytestmark = pytest.mark.gpu
+
+TOL = {0: 1e-6, 1: 1e-4}           # north_star tolerances per precision mode
+TIGHT = {0: 1e-11, 1: 3e-5}        # what the kernels actually deliver (regression guard)
+
+
+def ref_arrays(pn2, t):
+    """oracle.Tree -> the reference's Pack / Node arrays."""
+    lf, nd = t.leaves(), t.nodes()
+    leaf = np.zeros(t.nleaf, pn2.PACK)
+    btree = np.zeros(t.nnode, pn2.NODE)
+    for f in ("npart", "ipart", "width", "center"):
+        leaf[f] = lf[f]
+    for f in ("npart", "son", "split", "width", "center"):
+        btree[f] = nd[f]
+    return leaf, btree
+
+
+def let_arrays(pn2, lt):
+    a = lt.arrays()
+    rt = np.zeros(lt.nnode, pn2.RNODE)
+    for f in ("npart", "son", "width", "center", "M"):
+        rt[f] = a[f]
+    rb = np.zeros(lt.nbody, pn2.RBODY)
+    rb["pos"] = a["body"]
+    return rt, rb
+
+
+def run_mode_a(pn2, oracle, pos, prm_o, precision, with_images=True):
+    """One whole NP=1 force evaluation, device operators on the oracle's tree and lists."""
+    box = prm_o.box
+    t = oracle.Tree(pos, prm_o.maxleaf, [0, 0, 0], [box] * 3)
+    t.upward(prm_o.mass)
+    leaf, btree = ref_arrays(pn2, t)
+    prm = pn2.Params(prm_o.box, prm_o.rs, prm_o.cutoff, prm_o.soft, prm_o.theta, prm_o.mass, prm_o.maxleaf,
+                     prm_o.periodic, prm_o.longshort, precision)
+    ctx = pn2.Context(prm)
+    ps, pt, ms, mt = t.walk_local(prm_o)
+    remotes = []
+    nint_remote = 0
+    if with_images:
+        tc, tw = np.array([0.5 * box] * 3), np.array([box] * 3)
+        for sh in image_shifts(box):
+            lt = t.let_pack(prm_o, tc, tw, sh)
+            rps, rpt, rms_, rmt = t.walk_remote(lt, prm_o)
+            rt, rb = let_arrays(pn2, lt)
+            remotes.append((rt, rb, (rps, rpt), (rms_, rmt)))
+            nint_remote += int((rt["npart"][rps].astype(np.int64) * leaf["npart"][rpt - t.first_leaf]).sum())
+    acc = pn2.short_range_force_mode_a(ctx, t.pos, leaf, t.first_leaf, btree, t.first_node, (ps, pt), (ms, mt), remotes)
+    out = np.zeros_like(acc)
+    out[t.ids] = acc
+    nint_local = int((leaf["npart"][ps - t.first_leaf].astype(np.int64) * leaf["npart"][pt - t.first_leaf]).sum()
+                     - leaf["npart"][pt[ps == pt] - t.first_leaf].sum())
+    return out, ctx, t, (nint_local, nint_remote)
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+@pytest.mark.parametrize("tag", ["t04", "t12"])
+def test_small_full_step(pn2, oracle, small_pos, tag, precision):
+    g = load_golden(f"small_{tag}_np1.npz")
+    prm_o = oracle.make_params(float(g["box"]), int(g["nside"]), len(small_pos), float(g["mass"]), theta=float(g["theta"]))
+    acc, ctx, t, nint = run_mode_a(pn2, oracle, small_pos, prm_o, precision)
+    err = rms_rel(acc, g["acc"])          # against the UNMODIFIED reference's accelerations
+    print(f"small {tag} precision {precision}: rms rel err vs reference = {err:.3e}")
+    assert err < TOL[precision] and err < TIGHT[precision]
+    # interaction counter == the reference's counters
+    assert int(ctx.counters()[0]) == nint[0] + nint[1]
+    assert nint[0] == int(g["nint_local"][0]) and nint[1] == int(g["p2p_count_remote"][0])
+    # multipoles and local expansions against the reference dump (FP64 operators in both modes)
+    Ml, Mn = ctx.get_multipoles()
+    Ll, Ln = ctx.get_locals()
+    sc = np.abs(g["r0_node_M"]).max(0) + 1e-300
+    assert np.abs((Ml - g["r0_leaf_M"]) / sc).max() < 1e-12 and np.abs((Mn - g["r0_node_M"]) / sc).max() < 1e-12
+    scl = np.abs(g["r0_leaf_L"]).max(0) + 1e-300
+    assert np.abs((Ll - g["r0_leaf_L"]) / scl).max() < 1e-9
+    ctx.close()
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+@pytest.mark.parametrize("nside", [32, 16])
+def test_demo_full_step(pn2, oracle, demo_pos, nside, precision):
+    """configs[0]: demo/ic_lcdm.gdt2 with demo/lcdm_g2.run parameters (NSIDE 16 exercises M2L)."""
+    g = load_golden(f"demo_ns{nside}_np1.npz")
+    prm_o = oracle.make_params(float(g["box"]), nside, len(demo_pos), float(g["mass"]), maxleaf=8, theta=0.4)
+    acc, ctx, t, nint = run_mode_a(pn2, oracle, demo_pos, prm_o, precision)
+    err = rms_rel(acc, g["acc"])
+    print(f"demo nside {nside} precision {precision}: rms rel err vs reference = {err:.3e}")
+    assert err < TOL[precision] and err < TIGHT[precision]
+    assert nint[0] == int(g["nint_local"][0]) and nint[1] == int(g["p2p_count_remote"][0])
+    assert int(ctx.counters()[0]) == nint[0] + nint[1]
+    ctx.close()
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_batched_like_the_reference(pn2, oracle, small_pos, precision):
+    """The reference hands the worker 16384 pairs at a time (LEN_TASK, src/fmm.c:912): same result."""
+    g = load_golden("small_t04_np1.npz")
+    prm_o = oracle.make_params(float(g["box"]), int(g["nside"]), len(small_pos), float(g["mass"]), theta=0.4)
+    box = prm_o.box
+    t = oracle.Tree(small_pos, 8, [0, 0, 0], [box] * 3)
+    leaf, btree = ref_arrays(pn2, t)
+    prm = pn2.Params(prm_o.box, prm_o.rs, prm_o.cutoff, prm_o.soft, prm_o.theta, prm_o.mass, 8, 1, 1, precision)
+    ctx = pn2.Context(prm)
+    ps, pt, _, _ = t.walk_local(prm_o)
+    ctx.set_particles(t.pos)
+    ctx.set_tree(leaf, t.first_leaf, btree, t.first_node)
+    ctx.p2p_batch(ps, pt)
+    a1 = ctx.get_acc()
+    ctx.zero_acc()
+    for k in range(0, len(ps), 16384):
+        ctx.p2p_batch(ps[k:k + 16384], pt[k:k + 16384])
+    a2 = ctx.get_acc()
+    assert rms_rel(a2, a1) < (1e-14 if precision == 0 else 1e-6)
+    ref = np.zeros_like(a1)
+    t.eval_p2p(prm_o, ps, pt, ref)
+    assert rms_rel(a1, ref) < TIGHT[precision]
+    ctx.close()
+
+
+def test_edge_cases(pn2, oracle):
+    """Empty batch, empty leaves, a single leaf, coincident particles, bad ids."""
+    rng = np.random.default_rng(5)
+    box = 100.0
+    pos = rng.random((300, 3)) * box
+    pos[10] = pos[11]                       # coincident pair: contributes exactly 0 (dx = 0), no NaN
+    prm_o = oracle.make_params(box, 4, len(pos), 1.0, maxleaf=8, theta=0.5)
+    for precision in (0, 1):
+        t = oracle.Tree(pos, 8, [0, 0, 0], [box] * 3)
+        leaf, btree = ref_arrays(pn2, t)
+        prm = pn2.Params(prm_o.box, prm_o.rs, prm_o.cutoff, prm_o.soft, prm_o.theta, prm_o.mass, 8, 1, 1, precision)
+        ctx = pn2.Context(prm)
+        ctx.set_particles(t.pos)
+        ctx.set_tree(leaf, t.first_leaf, btree, t.first_node)
+        ctx.p2p_batch(np.zeros(0, np.int32), np.zeros(0, np.int32))          # empty batch is a no-op
+        assert np.all(ctx.get_acc() == 0.0)
+        ps, pt, ms, mt = t.walk_local(prm_o)
+        ctx.p2p_batch(ps, pt)
+        acc = ctx.get_acc()
+        assert np.isfinite(acc).all()
+        ref = np.zeros_like(acc)
+        t.eval_p2p(prm_o, ps, pt, ref)
+        assert rms_rel(acc, ref) < TIGHT[precision]
+        with pytest.raises(pn2.Pn2Error):
+            ctx.p2p_batch(np.array([t.last_node + 5], np.int32), np.array([t.first_leaf], np.int32))
+        ctx.close()
+    # one particle: a tree of one node and leaves, self pair only -> zero acceleration
+    one = np.array([[1.0, 2.0, 3.0]])
+    t = oracle.Tree(one, 8, [0, 0, 0], [box] * 3)
+    leaf, btree = ref_arrays(pn2, t)
+    ctx = pn2.Context(pn2.Params(box, 1.0, 4.5, 0.1, 0.4, 1.0, 8, 1, 1, 1))
+    ctx.set_particles(t.pos)
+    ctx.set_tree(leaf, t.first_leaf, btree, t.first_node)
+    ps, pt, ms, mt = t.walk_local(oracle.make_params(box, 4, 1, 1.0))
+    ctx.p2p_batch(ps, pt)
+    ctx.p2m_m2m()
+    ctx.l2l_l2p()
+    assert np.all(ctx.get_acc() == 0.0)
+    ctx.close()
+
+
+def test_call_order_errors(pn2):
+    ctx = pn2.Context(pn2.Params(1.0, 0.1, 0.45, 0.01, 0.4, 1.0, 8, 1, 1, 1))
+    with pytest.raises(pn2.Pn2Error):
+        ctx.p2m_m2m()                       # no tree yet
+    with pytest.raises(pn2.Pn2Error):
+        pn2.Context(pn2.Params(1.0, 0.1, 0.45, 0.01, 0.4, 1.0, 64, 1, 1, 1))   # maxleaf > 32
+    ctx.close()
