@@ -23,7 +23,7 @@ class Params(C.Structure):
 class Let(C.Structure):
     _fields_ = [("nnode", C.c_int), ("nbody", C.c_int), ("npart", C.POINTER(C.c_int)), ("son", C.POINTER(C.c_int)),
                 ("width", C.POINTER(C.c_double)), ("center", C.POINTER(C.c_double)), ("M", C.POINTER(C.c_double)),
-                ("body", C.POINTER(C.c_double))]
+                ("body", C.POINTER(C.c_double)), ("origin", C.POINTER(C.c_int))]
 
 
 def make_params(box, nside, npart_total, mass, maxleaf=8, theta=0.4, split=-1.0, soft=-1.0, periodic=1, longshort=1):
@@ -53,6 +53,8 @@ def lib():
         dp, ip, lp = C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_long)
         L.pno_tree_build.restype = C.c_void_p
         L.pno_tree_build.argtypes = [dp, lp, C.c_int, C.c_int, C.c_int, dp, dp]
+        L.pno_treeB_build.restype = C.c_void_p
+        L.pno_treeB_build.argtypes = [dp, C.c_int, C.c_int, C.c_int, dp, dp, dp, ip]
         L.pno_tree_free.argtypes = [C.c_void_p]
         L.pno_tree_sizes.argtypes = [C.c_void_p, ip, ip, ip, ip, ip]
         L.pno_tree_get_leaves.argtypes = [C.c_void_p, ip, ip, dp, dp, dp, dp]
@@ -187,6 +189,26 @@ class Tree:
         lib().pno_eval_m2l_remote(self.h, let.p, C.byref(prm), _ip(s), _ip(t), len(s))
 
 
+class TreeB(Tree):
+    """Mode B tree: CPU restatement of the device builder (pn2_tree.cu), in the reference id space."""
+
+    def __init__(self, pos, maxleaf, bl, br, direct0=0):
+        L = lib()
+        pin = np.ascontiguousarray(pos, np.float64)
+        n = pin.shape[0]
+        self.pos = np.zeros((n, 3))
+        order = np.zeros(n, np.int32)
+        bl = np.asarray(bl, np.float64)
+        br = np.asarray(br, np.float64)
+        self.h = L.pno_treeB_build(_dp(pin), n, maxleaf, direct0, _dp(bl), _dp(br), _dp(self.pos), _ip(order))
+        self.ids = order.astype(np.int64)
+        v = [C.c_int() for _ in range(5)]
+        L.pno_tree_sizes(self.h, *[C.byref(x) for x in v])
+        self.n, self.first_leaf, self.last_leaf, self.first_node, self.last_node = [x.value for x in v]
+        self.nleaf = self.last_leaf - self.first_leaf
+        self.nnode = self.last_node - self.first_node + 1
+
+
 class LetTree:
     """Pruned, flattened, displaced tree as packed by src/remotes.c:60-169."""
 
@@ -201,7 +223,7 @@ class LetTree:
         f = np.ctypeslib.as_array
         return {"npart": f(c.npart, (nn,)).copy(), "son": f(c.son, (2 * nn,)).reshape(nn, 2).copy(),
                 "width": f(c.width, (3 * nn,)).reshape(nn, 3).copy(), "center": f(c.center, (3 * nn,)).reshape(nn, 3).copy(),
-                "M": f(c.M, (NM * nn,)).reshape(nn, NM).copy(),
+                "M": f(c.M, (NM * nn,)).reshape(nn, NM).copy(), "origin": f(c.origin, (nn,)).copy(),
                 "body": f(c.body, (3 * nb,)).reshape(nb, 3).copy() if nb else np.zeros((0, 3))}
 
     def __del__(self):

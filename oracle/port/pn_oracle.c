@@ -523,6 +523,7 @@ static void let_grow(letbuf *b, int need_nodes, int need_bodies) {
         l->width = (double *)realloc(l->width, 3*b->ncap*sizeof(double));
         l->center = (double *)realloc(l->center, 3*b->ncap*sizeof(double));
         l->M = (double *)realloc(l->M, NM*b->ncap*sizeof(double));
+        l->origin = (int *)realloc(l->origin, b->ncap*sizeof(int));
     }
     if (l->nbody + need_bodies > b->bcap) {
         while (l->nbody + need_bodies > b->bcap) b->bcap = b->bcap ? 2*b->bcap : 4096;
@@ -536,6 +537,7 @@ static void pack_rec(const pno_tree *t, const double *pos, const pno_params *prm
     const double *c = Cn(t, ilocal), *w = Wd(t, ilocal);
     for (int d = 0; d < 3; d++) { l->center[3*isend+d] = c[d] + disp[d]; l->width[3*isend+d] = w[d]; }
     memcpy(l->M + NM*isend, Mp(t, ilocal), NM*sizeof(double));
+    l->origin[isend] = ilocal;
     if (is_leaf(t, ilocal)) {                      /* :65-95 */
         int lk = ilocal - t->first_leaf;
         l->npart[isend] = t->lf_npart[lk];
@@ -589,7 +591,7 @@ pno_let *pno_let_pack(const pno_tree *t, const double *pos, const pno_params *pr
 
 void pno_let_free(pno_let *l) {
     if (!l) return;
-    free(l->npart); free(l->son); free(l->width); free(l->center); free(l->M); free(l->body); free(l);
+    free(l->npart); free(l->son); free(l->width); free(l->center); free(l->M); free(l->body); free(l->origin); free(l);
 }
 
 /* remote walks, src/remotes.c:213-372 (P2P) and :405-552 (M2L), merged into one traversal */
@@ -802,4 +804,161 @@ void pno_force(const double *pos_in, int n, int P, const pno_params *prm, double
         pno_tree_free(tree[r]); free(pos[r]); free(acc[r]); free(ids[r]);
     }
     free(pos); free(acc); free(ids); free(tree); free(cnt); free(owner); free(dc); free(dw); free(pc); free(pw); free(splits); free(dstart);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Mode B tree: CPU restatement of the DEVICE builder (photons-2.0_b200/csrc/pn2_tree.cu).
+ * Same tree definition as src/fmm.c:30-264 (mean split, cycling direction, <= MAXLEAF -> leaf, boxes
+ * cut by the ancestors' splits) but built level by level: Morton pre-sort (21 bits per dimension of
+ * the domain box, stable), the mean from an exact integer sum of coordinates quantised to
+ * 2^-e (extent * 2^e < 2^36), stable partition "x > split goes right", breadth-first ids (per level:
+ * nodes in range order, son 0 before son 1).  Everything here must match the device bit for bit.
+ * ------------------------------------------------------------------------------------------ */
+static unsigned long long spread21(unsigned long long v) {
+    v &= 0x1fffffULL;
+    v = (v | v << 32) & 0x1f00000000ffffULL;
+    v = (v | v << 16) & 0x1f0000ff0000ffULL;
+    v = (v | v << 8) & 0x100f00f00f00f00fULL;
+    v = (v | v << 4) & 0x10c30c30c30c30c3ULL;
+    v = (v | v << 2) & 0x1249249249249249ULL;
+    return v;
+}
+typedef struct { unsigned long long key; int idx; } mkey;
+static int mkey_cmp(const void *a, const void *b) {
+    const mkey *x = (const mkey *)a, *y = (const mkey *)b;
+    if (x->key != y->key) return x->key < y->key ? -1 : 1;
+    return x->idx < y->idx ? -1 : (x->idx > y->idx);          /* stable */
+}
+
+pno_tree *pno_treeB_build(const double *pos_in, int n, int maxleaf, int direct0, const double bl[3], const double br[3],
+                          double *pos_out, int *order) {
+    init_tables();
+    pno_tree *t = (pno_tree *)calloc(1, sizeof *t);
+    t->n = n; t->maxleaf = maxleaf;
+    t->first_leaf = t->last_leaf = n;
+    t->first_node = n; t->last_node = n - 1;
+    if (n == 0) return t;
+    double ext[3], sc[3];
+    for (int d = 0; d < 3; d++) { ext[d] = br[d] - bl[d]; sc[d] = 2097152.0 / ext[d]; }
+    mkey *mk = (mkey *)malloc(n*sizeof(mkey));
+    for (int i = 0; i < n; i++) {
+        long long c[3];
+        for (int d = 0; d < 3; d++) {
+            double f = (pos_in[3*i+d] - bl[d]) * sc[d];
+            c[d] = f > 0.0 ? (long long)f : 0;
+            if (c[d] > 0x1fffff) c[d] = 0x1fffff;
+        }
+        mk[i].key = (spread21((unsigned long long)c[0]) << 2) | (spread21((unsigned long long)c[1]) << 1) | spread21((unsigned long long)c[2]);
+        mk[i].idx = i;
+    }
+    qsort(mk, n, sizeof(mkey), mkey_cmp);
+    double *pa = (double *)malloc(3*(size_t)n*sizeof(double)), *pb = (double *)malloc(3*(size_t)n*sizeof(double));
+    int *ia = (int *)malloc(n*sizeof(int)), *ib = (int *)malloc(n*sizeof(int));
+    for (int i = 0; i < n; i++) { ia[i] = mk[i].idx; for (int d = 0; d < 3; d++) pa[3*i+d] = pos_in[3*(size_t)mk[i].idx+d]; }
+    free(mk);
+    double emax = ext[0] > ext[1] ? ext[0] : ext[1];
+    if (ext[2] > emax) emax = ext[2];
+    int e2 = 0;
+    frexp(emax, &e2);
+    const double S = ldexp(1.0, 36 - e2), invS = ldexp(1.0, e2 - 36);
+    /* growable node / leaf records */
+    int ncap = 1024, lcap = 1024, nn = 1, nl = 0;
+    int *ns = (int *)malloc(ncap*sizeof(int)), *nc = (int *)malloc(ncap*sizeof(int)), *nson = (int *)malloc(2*ncap*sizeof(int));
+    double *nbox = (double *)malloc(6*ncap*sizeof(double)), *nsp = (double *)malloc(ncap*sizeof(double));
+    int *ls = (int *)malloc(lcap*sizeof(int)), *lc = (int *)malloc(lcap*sizeof(int));
+    double *lbox = (double *)malloc(6*lcap*sizeof(double));
+    ns[0] = 0; nc[0] = n;
+    for (int d = 0; d < 3; d++) { nbox[d] = bl[d]; nbox[3+d] = br[d]; }
+    int node0 = 0, cnt = 1, level = 0;
+    while (cnt > 0) {
+        int dir = (direct0 + level) % 3;
+        double lo = bl[dir];
+        int next0 = node0 + cnt, nnext = 0;
+        for (int k = 0; k < cnt; k++) {
+            int nd = node0 + k, a = ns[nd], c = nc[nd];
+            unsigned long long sum = 0;
+            for (int i = a; i < a + c; i++) {
+                double f = (pa[3*(size_t)i+dir] - lo) * S;
+                sum += f > 0.0 ? (unsigned long long)f : 0ULL;
+            }
+            double m = (double)sum / (double)c;
+            double split = lo + m * invS;
+            nsp[nd] = split;
+            /* stable partition into pb */
+            int nleft = 0;
+            for (int i = a; i < a + c; i++) { int fl = (c < 2) ? 1 : (pa[3*(size_t)i+dir] > split); if (!fl) nleft++; }
+            int pl = a, pr = a + nleft;
+            for (int i = a; i < a + c; i++) {
+                int fl = (c < 2) ? 1 : (pa[3*(size_t)i+dir] > split);
+                int dst = fl ? pr++ : pl++;
+                pb[3*(size_t)dst] = pa[3*(size_t)i]; pb[3*(size_t)dst+1] = pa[3*(size_t)i+1]; pb[3*(size_t)dst+2] = pa[3*(size_t)i+2];
+                ib[dst] = ia[i];
+            }
+            int cn[2] = {nleft, c - nleft}, st[2] = {a, a + nleft};
+            for (int s = 0; s < 2; s++) {
+                double cb[6];
+                for (int d = 0; d < 6; d++) cb[d] = nbox[6*(size_t)nd+d];
+                if (s == 0) cb[3+dir] = split; else cb[dir] = split;
+                if (cn[s] <= maxleaf) {
+                    if (nl == lcap) { lcap *= 2; ls = (int *)realloc(ls, lcap*sizeof(int)); lc = (int *)realloc(lc, lcap*sizeof(int)); lbox = (double *)realloc(lbox, 6*(size_t)lcap*sizeof(double)); }
+                    ls[nl] = st[s]; lc[nl] = cn[s];
+                    for (int d = 0; d < 6; d++) lbox[6*(size_t)nl+d] = cb[d];
+                    nson[2*nd+s] = -(nl + 2);
+                    nl++;
+                } else {
+                    int ni = next0 + nnext;
+                    if (ni >= ncap) { ncap *= 2; ns = (int *)realloc(ns, ncap*sizeof(int)); nc = (int *)realloc(nc, ncap*sizeof(int)); nson = (int *)realloc(nson, 2*(size_t)ncap*sizeof(int)); nbox = (double *)realloc(nbox, 6*(size_t)ncap*sizeof(double)); nsp = (double *)realloc(nsp, ncap*sizeof(double)); }
+                    ns[ni] = st[s]; nc[ni] = cn[s];
+                    for (int d = 0; d < 6; d++) nbox[6*(size_t)ni+d] = cb[d];
+                    nson[2*nd+s] = ni;
+                    nnext++;
+                }
+            }
+        }
+        /* particles of finished leaves do not move */
+        /* (pb was only written inside this level's node ranges) */
+        {
+            /* copy back the ranges of this level's nodes */
+            for (int k = 0; k < cnt; k++) {
+                int nd = node0 + k, a = ns[nd], c = nc[nd];
+                memcpy(pa + 3*(size_t)a, pb + 3*(size_t)a, 3*(size_t)c*sizeof(double));
+                memcpy(ia + a, ib + a, c*sizeof(int));
+            }
+        }
+        node0 = next0; cnt = nnext; nn = next0 + nnext; level++;
+        if (level > 200) { fprintf(stderr, "pn_oracle: treeB deeper than 200 levels\n"); exit(3); }
+    }
+    nn = node0;
+    /* fill the pno_tree in the reference id space: leaves n..n+nl-1, nodes n+nl..n+nl+nn-1 */
+    t->leafcap = nl; t->nodecap = nn;
+    t->first_leaf = n; t->last_leaf = n + nl; t->first_node = n + nl; t->last_node = n + nl + nn - 1;
+    t->lf_npart = (int *)calloc(nl, sizeof(int)); t->lf_ipart = (int *)calloc(nl, sizeof(int));
+    t->lf_center = (double *)calloc(3*(size_t)nl, sizeof(double)); t->lf_width = (double *)calloc(3*(size_t)nl, sizeof(double));
+    t->lf_M = (double *)calloc(NM*(size_t)nl, sizeof(double)); t->lf_L = (double *)calloc(NM*(size_t)nl, sizeof(double));
+    t->nd_npart = (int *)calloc(nn, sizeof(int)); t->nd_son = (int *)malloc(2*(size_t)nn*sizeof(int));
+    t->nd_split = (double *)calloc(nn, sizeof(double));
+    t->nd_center = (double *)calloc(3*(size_t)nn, sizeof(double)); t->nd_width = (double *)calloc(3*(size_t)nn, sizeof(double));
+    t->nd_M = (double *)calloc(NM*(size_t)nn, sizeof(double)); t->nd_L = (double *)calloc(NM*(size_t)nn, sizeof(double));
+    for (int k = 0; k < nl; k++) {
+        t->lf_npart[k] = lc[k]; t->lf_ipart[k] = ls[k];
+        for (int d = 0; d < 3; d++) {
+            t->lf_center[3*k+d] = 0.5 * (lbox[6*(size_t)k+3+d] + lbox[6*(size_t)k+d]);
+            t->lf_width[3*k+d] = lbox[6*(size_t)k+3+d] - lbox[6*(size_t)k+d];
+        }
+    }
+    for (int k = 0; k < nn; k++) {
+        t->nd_npart[k] = nc[k]; t->nd_split[k] = nsp[k];
+        for (int d = 0; d < 3; d++) {
+            t->nd_center[3*k+d] = 0.5 * (nbox[6*(size_t)k+3+d] + nbox[6*(size_t)k+d]);
+            t->nd_width[3*k+d] = nbox[6*(size_t)k+3+d] - nbox[6*(size_t)k+d];
+        }
+        for (int s = 0; s < 2; s++) {
+            int ch = nson[2*k+s];
+            t->nd_son[2*k+s] = ch >= 0 ? t->first_node + ch : t->first_leaf + (-(ch + 2));
+        }
+    }
+    if (pos_out) memcpy(pos_out, pa, 3*(size_t)n*sizeof(double));
+    if (order) memcpy(order, ia, n*sizeof(int));
+    free(pa); free(pb); free(ia); free(ib); free(ns); free(nc); free(nson); free(nbox); free(nsp); free(ls); free(lc); free(lbox);
+    return t;
 }

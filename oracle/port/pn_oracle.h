@@ -74,6 +74,7 @@ typedef struct {
     double *center;  /* [3*nnode] */
     double *M;       /* [20*nnode] */
     double *body;    /* [3*nbody] */
+    int *origin;     /* [nnode] local id of the packed cell (checker convenience, not sent by the reference) */
 } pno_let;
 pno_let *pno_let_pack(const pno_tree *t, const double *pos, const pno_params *prm, const double tcenter[3],
                       const double twidth[3], const double displace[3]);
@@ -88,6 +89,12 @@ void pno_eval_m2l_remote(pno_tree *t, const pno_let *l, const pno_params *prm, c
 /* boxes of the nranks domains for the initial equal-load decomposition; center/width are [3*nranks] by RANK */
 void pno_domain_boxes(int nranks, double box, double *center, double *width, int *direct_start, double *splits /* [2*nranks-1] */);
 int  pno_domain_of(const double x[3], int nranks, const double *splits);  /* rank owning position x */
+
+/* ---- Mode B tree: restatement of the DEVICE builder (photons-2.0_b200/csrc/pn2_tree.cu); returns a pno_tree in the
+ *      reference id space (leaves n.., nodes n+nleaf..; breadth-first numbering) so every walker / operator above works
+ *      on it.  pos_out [3n]: positions in tree order; order [n]: input index of the k-th particle in tree order ---- */
+pno_tree *pno_treeB_build(const double *pos_in, int n, int maxleaf, int direct0, const double bl[3], const double br[3],
+                          double *pos_out, int *order);
 
 /* ---- whole short-range force evaluation, nranks simulated sequentially in one process
  *      (src/photoNs.c:83-116 without PM).  acc is [3n] in INPUT order.  counters[8]:

@@ -299,14 +299,12 @@ __global__ void int_to_long_kernel(int n, const int *__restrict__ in, long *__re
     else if (i == n) o[i] = 0;
 }
 
-// out->seg_sink = h->ic, out->seg_off = h->la, out->src = h->ub  (valid until the next batch call)
 int pn2_build_csr(pn2_ctx *h, const int *h_s, const int *h_t, long n, int remote_src, int sinks_may_be_nodes, CsrList *out) {
     out->nseg = 0;
     if (n == 0) return PN2_OK;
     if (n < 0 || !h_s || !h_t) { pn2_set_error("pn2: bad batch"); return PN2_ERR_ARG; }
     if (n >= (1L << 31)) { pn2_set_error("pn2: batch of %ld pairs; split it (the reference uses 16384)", n); return PN2_ERR_ARG; }
-    PN2_TRY(h->ia.ensure(n)); PN2_TRY(h->ib.ensure(n)); PN2_TRY(h->ic.ensure(n + 1)); PN2_TRY(h->id_.ensure(n + 2));
-    PN2_TRY(h->ua.ensure(n)); PN2_TRY(h->ub.ensure(n)); PN2_TRY(h->la.ensure(n + 2));
+    PN2_TRY(h->ia.ensure(n)); PN2_TRY(h->ib.ensure(n + 1)); PN2_TRY(h->id_.ensure(n + 2)); PN2_TRY(h->ua.ensure(n));
     cudaStream_t st = h->stream;
     CUDA_TRY(cudaMemcpyAsync(h->ia.p, h_s, n * sizeof(int), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(h->ib.p, h_t, n * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -323,29 +321,40 @@ int pn2_build_csr(pn2_ctx *h, const int *h_s, const int *h_t, long n, int remote
                                              h->first_node, sinks_may_be_nodes ? h->nnode : 0, h->ua.p, tcell, bad);
     h->launches++;
     KERNEL_CHECK();
-    // stable sort by sink cell; sources keep list order within a sink
+    CUDA_TRY(cudaStreamSynchronize(st));
+    int hb = 0;
+    CUDA_TRY(cudaMemcpy(&hb, bad, sizeof(int), cudaMemcpyDeviceToHost));
+    if (hb != 0) { pn2_set_error("pn2: %d ids of the batch are outside the tree", hb); return PN2_ERR_ARG; }
+    return pn2_csr_from_device_pairs(h, tcell, h->ua.p, n, out);
+}
+
+// device pairs (sink cell, source entry) -> CSR by sink.  Stable radix sort by sink cell (sources keep
+// their list order within a sink), run-length encode, exclusive scan.  tcell must not alias ia/ib/ic/la/ub.
+// out->seg_sink = h->ic, out->seg_off = h->la, out->src = h->ub (valid until the next call).
+int pn2_csr_from_device_pairs(pn2_ctx *h, int *tcell, unsigned *scell, long n, CsrList *out) {
+    out->nseg = 0;
+    if (n == 0) return PN2_OK;
+    cudaStream_t st = h->stream;
+    PN2_TRY(h->ia.ensure(n)); PN2_TRY(h->ib.ensure(n + 1)); PN2_TRY(h->ic.ensure(n + 1));
+    PN2_TRY(h->ub.ensure(n)); PN2_TRY(h->la.ensure(n + 2)); PN2_TRY(h->b_scal.ensure(16));
     size_t tb = 0, tb2 = 0, tb3 = 0;
     int bits = 1;
     while ((1L << bits) < (long)h->ncell + 1 && bits < 31) bits++;
-    int *tsorted = h->ia.p;    // reuse
-    cub::DeviceRadixSort::SortPairs(nullptr, tb, tcell, tsorted, h->ua.p, h->ub.p, (int)n, 0, bits, st);
-    int *runs = h->ib.p;       // run lengths
-    int *nruns = h->id_.p + n; // device scalar
+    int *tsorted = h->ia.p;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, tcell, tsorted, scell, h->ub.p, (int)n, 0, bits, st);
+    int *runs = h->ib.p;
+    int *nruns = h->b_scal.p + 8;
     cub::DeviceRunLengthEncode::Encode(nullptr, tb2, tsorted, h->ic.p, runs, nruns, (int)n, st);
     cub::DeviceScan::ExclusiveSum(nullptr, tb3, (long *)nullptr, (long *)nullptr, (int)n + 1, st);
     size_t need = tb > tb2 ? tb : tb2;
     if (tb3 > need) need = tb3;
     PN2_TRY(h->tmp.ensure(need + 16));
-    cub::DeviceRadixSort::SortPairs(h->tmp.p, tb, tcell, tsorted, h->ua.p, h->ub.p, (int)n, 0, bits, st);
+    cub::DeviceRadixSort::SortPairs(h->tmp.p, tb, tcell, tsorted, scell, h->ub.p, (int)n, 0, bits, st);
     cub::DeviceRunLengthEncode::Encode(h->tmp.p, tb2, tsorted, h->ic.p, runs, nruns, (int)n, st);
     h->launches += 4;
-    int hn[2] = {0, 0};
-    CUDA_TRY(cudaMemcpyAsync(&hn[0], nruns, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(&hn[1], bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    int nseg = 0;
+    CUDA_TRY(cudaMemcpyAsync(&nseg, nruns, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    if (hn[1] != 0) { pn2_set_error("pn2: %d ids of the batch are outside the tree", hn[1]); return PN2_ERR_ARG; }
-    int nseg = hn[0];
-    // offsets: exclusive scan of the run lengths into long
     int_to_long_kernel<<<(unsigned)((nseg + 256) / 256), 256, 0, st>>>(nseg, runs, h->la.p);
     cub::DeviceScan::ExclusiveSum(h->tmp.p, tb3, h->la.p, h->la.p, nseg + 1, st);
     h->launches += 2;

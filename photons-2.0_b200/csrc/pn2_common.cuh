@@ -119,6 +119,34 @@ struct pn2_ctx {
     DBuf<unsigned long long> counters;   // [8]
     double timings[8] = {0};
     bool have_particles = false, have_tree = false, have_remote = false;
+
+    // ---- Mode B (device-built tree / lists) ----
+    DBuf<int> order;                 // [n] caller index of the k-th particle in tree order
+    DBuf<int> parent, depth;         // [ncell]
+    DBuf<double> b_pos2;             // ping-pong of pos during the build
+    DBuf<int> b_idx2, b_seg, b_seg2;
+    DBuf<unsigned long long> b_q;    // quantised coordinates / their scan, morton keys
+    DBuf<unsigned long long> b_key2;
+    DBuf<int> b_f;                   // flags / their scan
+    DBuf<int> n_start, n_count, n_son, n_depth, l_start, l_count;   // build-time node / leaf records
+    DBuf<double> n_box, n_split, l_box;                              // [cap][6] lo, hi
+    DBuf<unsigned long long> b_cnt;  // per-level child counts (leaf | node << 32) and scan
+    DBuf<int> b_scal;                // device scalars
+    DBuf<unsigned> m2l_pairs;        // [cap][2] (sink cell, src cell | image << 26), appended by the walk
+    size_t m2l_cap = 0;
+    DBuf<long> lst_off;              // dump mode: per-leaf offsets
+    DBuf<unsigned> lst_src;
+    DBuf<int> lst_sink;
+    long lst_nsrc = 0;
+    CsrList m2l_csr{};               // CSR view of the last step's M2L list (buffers ia/ic/la/ub)
+    pn2_domain dom{};
+    pn2_step_info info{};
+    bool have_step = false;
+    // multi-rank
+    int rank = 0, nranks = 1;
+    std::vector<pn2_domain> all_dom;
+    void *nccl = nullptr;
+    cudaEvent_t ev[8] = {nullptr};
 };
 
 // ---- kernels / launchers implemented across the .cu files ----
@@ -130,4 +158,7 @@ int pn2_launch_l2l_l2p(pn2_ctx *h);
 int pn2_launch_relpos(pn2_ctx *h, const double *pos, const LeafDesc *desc, int ncell_leaf, float4 *rel, int n);
 int pn2_build_csr(pn2_ctx *h, const int *h_s, const int *h_t, long n, int remote_src, int sinks_may_be_nodes, CsrList *out);
 void pn2_modeb_release(pn2_ctx *h);
+int pn2_csr_from_device_pairs(pn2_ctx *h, int *tcell, unsigned *scell, long n, CsrList *out);
+int pn2_tree_build_device(pn2_ctx *h, const double *d_pos_in, int n, const pn2_domain *dom);
+int pn2_walk_fused(pn2_ctx *h, int dump);
 void pn2_init_consts(pn2_ctx *h);

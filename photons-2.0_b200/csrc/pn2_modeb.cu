@@ -1,12 +1,223 @@
-// pn2_modeb.cu -- Mode B (device tree, device lists, images, LET): placeholder until the builder lands.
+// pn2_modeb.cu -- Mode B orchestration: one whole short-range force evaluation on the device
+// (fmm_construct + fmm_prepare + fmm_task + fmm_ext of src/photoNs.c:97-116, PM excluded):
+//   tree build (pn2_tree.cu) -> P2M + M2M -> fused walk + P2P incl. periodic images (pn2_walk.cu)
+//   -> M2L over the pairs the walk found -> L2L + L2P -> accelerations back in caller order.
+#include <cub/cub.cuh>
 #include "pn2_common.cuh"
-void pn2_modeb_release(pn2_ctx *h) { (void)h; }
-#define NOTYET(name) { pn2_set_error(name ": Mode B is not built yet"); return PN2_ERR_STATE; }
-extern "C" int pn2_force_step(pn2_ctx *, const double *, size_t, int, const pn2_domain *, double *, size_t) NOTYET("pn2_force_step")
-extern "C" int pn2_force_step_device(pn2_ctx *, const double *, int, const pn2_domain *, double *) NOTYET("pn2_force_step_device")
-extern "C" int pn2_set_comm(pn2_ctx *, int, int, const pn2_domain *, void *) NOTYET("pn2_set_comm")
-extern "C" int pn2_get_step_info(pn2_ctx *, pn2_step_info *) NOTYET("pn2_get_step_info")
-extern "C" int pn2_get_order(pn2_ctx *, int *, int) NOTYET("pn2_get_order")
-extern "C" int pn2_get_cells(pn2_ctx *, double *, int *, int *, double *, double *) NOTYET("pn2_get_cells")
-extern "C" int pn2_get_lists(pn2_ctx *, int, long *, long *, int *, long *, int *) NOTYET("pn2_get_lists")
-extern "C" int pn2_get_timings(pn2_ctx *, double *) NOTYET("pn2_get_timings")
+
+void pn2_modeb_release(pn2_ctx *h) {
+    h->order.release(); h->parent.release(); h->depth.release(); h->b_pos2.release(); h->b_idx2.release();
+    h->b_seg.release(); h->b_seg2.release(); h->b_q.release(); h->b_key2.release(); h->b_f.release();
+    h->n_start.release(); h->n_count.release(); h->n_son.release(); h->n_depth.release(); h->l_start.release();
+    h->l_count.release(); h->n_box.release(); h->n_split.release(); h->l_box.release(); h->b_cnt.release();
+    h->b_scal.release(); h->m2l_pairs.release(); h->lst_off.release(); h->lst_src.release(); h->lst_sink.release();
+    for (int i = 0; i < 8; i++) if (h->ev[i]) { cudaEventDestroy(h->ev[i]); h->ev[i] = nullptr; }
+}
+
+__global__ void scatter_acc_kernel(int n, const double *__restrict__ acc, const int *__restrict__ order,
+                                   double *__restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    size_t o = (size_t)order[i];
+    out[3 * o] = acc[3 * (size_t)i];
+    out[3 * o + 1] = acc[3 * (size_t)i + 1];
+    out[3 * o + 2] = acc[3 * (size_t)i + 2];
+}
+__global__ void iota_kernel(int n, int *o) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) o[i] = i;
+}
+
+static int ensure_events(pn2_ctx *h) {
+    for (int i = 0; i < 8; i++)
+        if (!h->ev[i]) CUDA_TRY(cudaEventCreate(&h->ev[i]));
+    return PN2_OK;
+}
+
+extern "C" int pn2_force_step_device(pn2_ctx *h, const double *d_pos, int n, const pn2_domain *dom, double *d_acc) {
+    if (!h || n < 0 || !dom || (n > 0 && (!d_pos || !d_acc))) { pn2_set_error("pn2_force_step_device: bad argument"); return PN2_ERR_ARG; }
+    for (int d = 0; d < 3; d++)
+        if (!(dom->hi[d] > dom->lo[d])) { pn2_set_error("pn2_force_step_device: empty domain box"); return PN2_ERR_ARG; }
+    if (dom->direct0 < 0 || dom->direct0 > 2) { pn2_set_error("pn2_force_step_device: direct0 must be 0..2"); return PN2_ERR_ARG; }
+    CUDA_TRY(cudaSetDevice(h->device));
+    PN2_TRY(ensure_events(h));
+    cudaStream_t st = h->stream;
+    h->have_step = false;
+    memset(&h->info, 0, sizeof h->info);
+    CUDA_TRY(cudaEventRecord(h->ev[0], st));
+    PN2_TRY(pn2_tree_build_device(h, d_pos, n, dom));
+    CUDA_TRY(cudaEventRecord(h->ev[1], st));
+    h->info.n = n; h->info.nleaf = h->nleaf; h->info.nnode = h->nnode; h->info.nlevel = h->nlevel;
+    if (n == 0) { h->have_step = true; return PN2_OK; }
+    // upward pass
+    if (h->prm.precision == PN2_FP32) PN2_TRY(pn2_launch_relpos(h, h->pos.p, h->desc.p, h->nleaf, h->rel.p, n));
+    PN2_TRY(pn2_launch_p2m(h));
+    PN2_TRY(pn2_launch_m2m(h));
+    CUDA_TRY(cudaEventRecord(h->ev[2], st));
+    // fused walk + P2P (local pairs and the 26 periodic images)
+    if (h->m2l_cap == 0) {
+        size_t cap = 4u << 20;
+        PN2_TRY(h->m2l_pairs.ensure(2 * cap));
+        h->m2l_cap = cap;
+    }
+    unsigned long long cnt[4];
+    for (int attempt = 0;; attempt++) {
+        CUDA_TRY(cudaMemsetAsync(h->counters.p, 0, 8 * sizeof(unsigned long long), st));
+        PN2_TRY(pn2_walk_fused(h, 0));
+        CUDA_TRY(cudaMemcpyAsync(cnt, h->counters.p, sizeof cnt, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (cnt[3]) { pn2_set_error("pn2: walk stack overflow (pathological particle distribution)"); return PN2_ERR_NOMEM; }
+        if (cnt[1] <= h->m2l_cap) break;
+        if (attempt >= 2) { pn2_set_error("pn2: M2L list does not fit"); return PN2_ERR_NOMEM; }
+        // the M2L pair buffer was too small: grow it and redo the walk from clean accelerations
+        size_t cap = (size_t)cnt[1] + (size_t)cnt[1] / 4 + 1024;
+        h->m2l_pairs.release();
+        PN2_TRY(h->m2l_pairs.ensure(2 * cap));
+        h->m2l_cap = cap;
+        CUDA_TRY(cudaMemsetAsync(h->acc.p, 0, 3 * (size_t)n * sizeof(double), st));
+    }
+    h->info.n_interactions = (int64_t)cnt[0]; h->info.n_m2l_pairs = (int64_t)cnt[1]; h->info.n_p2p_pairs = (int64_t)cnt[2];
+    CUDA_TRY(cudaEventRecord(h->ev[3], st));
+    // M2L
+    if (cnt[1] > 0) {
+        CsrList list;
+        PN2_TRY(pn2_csr_from_device_pairs(h, (int *)h->m2l_pairs.p, h->m2l_pairs.p + h->m2l_cap, (long)cnt[1], &list));
+        PN2_TRY(pn2_launch_m2l(h, list, h->geom.p, h->M.p));
+    }
+    CUDA_TRY(cudaEventRecord(h->ev[4], st));
+    PN2_TRY(pn2_launch_l2l_l2p(h));
+    scatter_acc_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, h->acc.p, h->order.p, d_acc);
+    h->launches++;
+    CUDA_TRY(cudaEventRecord(h->ev[5], st));
+    KERNEL_CHECK();
+    h->have_step = true;
+    return PN2_OK;
+}
+
+extern "C" int pn2_force_step(pn2_ctx *h, const double *pos, size_t pos_stride, int n, const pn2_domain *dom, double *acc,
+                              size_t acc_stride) {
+    if (!h || n < 0 || (n > 0 && (!pos || !acc)) || pos_stride < 24 || acc_stride < 24 || pos_stride % 8 || acc_stride % 8) {
+        pn2_set_error("pn2_force_step: bad argument");
+        return PN2_ERR_ARG;
+    }
+    CUDA_TRY(cudaSetDevice(h->device));
+    static thread_local DBuf<double> in, out;
+    PN2_TRY(in.ensure(3 * (size_t)n + 3)); PN2_TRY(out.ensure(3 * (size_t)n + 3));
+    if (n > 0) CUDA_TRY(cudaMemcpy2DAsync(in.p, 24, pos, pos_stride, 24, n, cudaMemcpyHostToDevice, h->stream));
+    PN2_TRY(pn2_force_step_device(h, in.p, n, dom, out.p));
+    if (n > 0) CUDA_TRY(cudaMemcpy2DAsync(acc, acc_stride, out.p, 24, 24, n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return PN2_OK;
+}
+
+extern "C" int pn2_set_comm(pn2_ctx *h, int rank, int nranks, const pn2_domain *all, void *comm) {
+    if (!h || nranks < 1 || rank < 0 || rank >= nranks || !all) { pn2_set_error("pn2_set_comm: bad argument"); return PN2_ERR_ARG; }
+    h->rank = rank; h->nranks = nranks; h->nccl = comm;
+    h->all_dom.assign(all, all + nranks);
+    if (nranks > 1) { pn2_set_error("pn2_set_comm: multi-rank LET exchange is not built yet"); return PN2_ERR_STATE; }
+    return PN2_OK;
+}
+
+static int need_step(pn2_ctx *h, const char *who) {
+    if (!h) { pn2_set_error("pn2: null context"); return PN2_ERR_ARG; }
+    if (!h->have_step) { pn2_set_error("%s: no completed pn2_force_step on this context", who); return PN2_ERR_STATE; }
+    CUDA_TRY(cudaSetDevice(h->device));
+    return PN2_OK;
+}
+
+extern "C" int pn2_get_step_info(pn2_ctx *h, pn2_step_info *info) {
+    PN2_TRY(need_step(h, "pn2_get_step_info"));
+    if (!info) { pn2_set_error("pn2_get_step_info: null"); return PN2_ERR_ARG; }
+    *info = h->info;
+    return PN2_OK;
+}
+
+extern "C" int pn2_get_order(pn2_ctx *h, int *order, int n) {
+    PN2_TRY(need_step(h, "pn2_get_order"));
+    if (n != h->n || (!order && n > 0)) { pn2_set_error("pn2_get_order: n mismatch"); return PN2_ERR_ARG; }
+    if (n > 0) CUDA_TRY(cudaMemcpyAsync(order, h->order.p, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return PN2_OK;
+}
+
+extern "C" int pn2_get_cells(pn2_ctx *h, double *geom, int *son, int *range, double *M, double *L) {
+    PN2_TRY(need_step(h, "pn2_get_cells"));
+    size_t nc = (size_t)h->ncell;
+    cudaStream_t st = h->stream;
+    if (nc == 0) return PN2_OK;
+    if (geom) CUDA_TRY(cudaMemcpyAsync(geom, h->geom.p, 6 * nc * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (son) CUDA_TRY(cudaMemcpyAsync(son, h->son.p, 2 * nc * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (M) CUDA_TRY(cudaMemcpyAsync(M, h->M.p, NM * nc * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (L) CUDA_TRY(cudaMemcpyAsync(L, h->L.p, NM * nc * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (range) {
+        std::vector<LeafDesc> d(nc);
+        CUDA_TRY(cudaMemcpyAsync(d.data(), h->desc.p, nc * sizeof(LeafDesc), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        for (size_t c = 0; c < nc; c++) { range[2 * c] = d[c].first; range[2 * c + 1] = d[c].npart; }
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return PN2_OK;
+}
+
+extern "C" int pn2_get_lists(pn2_ctx *h, int kind, long *nseg, long *nsrc, int *seg_sink, long *seg_off, int *src) {
+    PN2_TRY(need_step(h, "pn2_get_lists"));
+    if (!nseg || !nsrc || (kind != 0 && kind != 1)) { pn2_set_error("pn2_get_lists: bad argument"); return PN2_ERR_ARG; }
+    cudaStream_t st = h->stream;
+    if (kind == 1) {
+        long n = (long)h->info.n_m2l_pairs;
+        CsrList list;
+        list.nseg = 0;
+        if (n > 0) {
+            // sort a copy: the pair buffer keeps its emission order
+            PN2_TRY(h->id_.ensure(n + 2)); PN2_TRY(h->ua.ensure(n));
+            CUDA_TRY(cudaMemcpyAsync(h->id_.p, h->m2l_pairs.p, n * sizeof(int), cudaMemcpyDeviceToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(h->ua.p, h->m2l_pairs.p + h->m2l_cap, n * sizeof(unsigned), cudaMemcpyDeviceToDevice, st));
+            PN2_TRY(pn2_csr_from_device_pairs(h, h->id_.p, h->ua.p, n, &list));
+        }
+        *nseg = list.nseg; *nsrc = n;
+        if (seg_sink && seg_off && src && list.nseg > 0) {
+            CUDA_TRY(cudaMemcpyAsync(seg_sink, list.seg_sink, list.nseg * sizeof(int), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(seg_off, list.seg_off, (list.nseg + 1) * sizeof(long), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(src, list.src, n * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        } else if (seg_off) seg_off[0] = 0;
+        CUDA_TRY(cudaStreamSynchronize(st));
+        return PN2_OK;
+    }
+    // P2P lists are never materialised by the product step: replay the walk in dump mode (count, scan, fill)
+    int nl = h->nleaf;
+    long total = (long)h->info.n_p2p_pairs;
+    *nseg = nl; *nsrc = total;
+    if (!seg_sink || !seg_off || !src) return PN2_OK;
+    PN2_TRY(h->lst_off.ensure(nl + 2)); PN2_TRY(h->lst_src.ensure(total + 1));
+    CUDA_TRY(cudaMemsetAsync(h->lst_off.p, 0, (nl + 2) * sizeof(long), st));
+    PN2_TRY(pn2_walk_fused(h, 1));
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, h->lst_off.p, h->lst_off.p, nl + 1, st);
+    PN2_TRY(h->tmp.ensure(tb + 16));
+    cub::DeviceScan::ExclusiveSum(h->tmp.p, tb, h->lst_off.p, h->lst_off.p, nl + 1, st);
+    h->launches++;
+    PN2_TRY(pn2_walk_fused(h, 2));
+    CUDA_TRY(cudaMemcpyAsync(seg_off, h->lst_off.p, (nl + 1) * sizeof(long), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(src, h->lst_src.p, total * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int i = 0; i < nl; i++) seg_sink[i] = i;
+    if (seg_off[nl] != total) { pn2_set_error("pn2_get_lists: replay found %ld pairs, the step %ld", seg_off[nl], total); return PN2_ERR_STATE; }
+    return PN2_OK;
+}
+
+extern "C" int pn2_get_timings(pn2_ctx *h, double ms[8]) {
+    PN2_TRY(need_step(h, "pn2_get_timings"));
+    if (!ms) { pn2_set_error("pn2_get_timings: null"); return PN2_ERR_ARG; }
+    for (int i = 0; i < 8; i++) ms[i] = 0.0;
+    if (h->n == 0) return PN2_OK;
+    CUDA_TRY(cudaEventSynchronize(h->ev[5]));
+    for (int i = 0; i < 5; i++) {
+        float t = 0;
+        CUDA_TRY(cudaEventElapsedTime(&t, h->ev[i], h->ev[i + 1]));
+        ms[i] = t;
+    }
+    float t = 0;
+    CUDA_TRY(cudaEventElapsedTime(&t, h->ev[0], h->ev[5]));
+    ms[6] = t;
+    return PN2_OK;
+}

@@ -1,0 +1,346 @@
+// pn2_tree.cu -- Mode B: the local k-d tree of src/fmm.c:30-264 built on the device.
+//
+// Same tree definition as the reference (build_kdtree / center_kdtree): binary splits at the coordinate
+// MEAN of the node's particles, direction cycling x->y->z from direct_local_start, a child with
+// <= MAXLEAF particles becomes a leaf, boxes are the domain box cut by the ancestors' splits.  The
+// reference builds it by depth-first recursion with an in-place Hoare partition and a sequential
+// FP64 sum (inherently serial); here it is built LEVEL BY LEVEL over all nodes of a depth at once:
+//
+//   0. Morton pre-sort: 63-bit keys (21 bits per dimension of the domain box), LSD radix sort.
+//      It fixes the particle order inside every leaf (stable partitions keep Morton order).
+//   per level, direction dir = (direct0 + level) % 3:
+//   1. q_i = trunc((x_i[dir] - lo[dir]) * 2^e) as uint64, exclusive prefix sum over all particles;
+//      a node's coordinate sum is a difference of two prefix values: exact integers, independent of
+//      summation order, so a CPU restatement reproduces every split bit for bit (oracle: pno_treeB_build).
+//   2. split = lo[dir] + (sum / count) * 2^-e;  flag_i = x_i[dir] > split (the reference's "> mean goes right",
+//      src/fmm.c:60-72); exclusive prefix sum of the flags gives every particle its slot in a STABLE
+//      partition of its node's range.
+//   3. children: count <= MAXLEAF -> leaf, else node of the next level; ids are handed out by prefix
+//      sums over the level (breadth-first numbering, deterministic).
+//   4. scatter particles (position, caller index, next node) to the other buffer.
+//
+// All FP64 expressions that decide tree shape use explicit round-to-nearest intrinsics (no FMA
+// contraction) in the order the oracle uses.
+#include <cub/cub.cuh>
+#include "pn2_common.cuh"
+
+#define TB 256
+static inline unsigned nb(long n) { return (unsigned)((n + TB - 1) / TB); }
+
+__device__ __forceinline__ unsigned long long spread21(unsigned long long v) {
+    v &= 0x1fffffULL;
+    v = (v | v << 32) & 0x1f00000000ffffULL;
+    v = (v | v << 16) & 0x1f0000ff0000ffULL;
+    v = (v | v << 8) & 0x100f00f00f00f00fULL;
+    v = (v | v << 4) & 0x10c30c30c30c30c3ULL;
+    v = (v | v << 2) & 0x1249249249249249ULL;
+    return v;
+}
+
+// Morton key: cell index floor((x - lo) * (2^21 / (hi - lo))) per dimension, clamped to [0, 2^21)
+__global__ void morton_kernel(int n, const double *__restrict__ pos, double lox, double loy, double loz, double sx,
+                              double sy, double sz, unsigned long long *__restrict__ key, int *__restrict__ idx) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double fx = __dmul_rn(__dsub_rn(pos[3 * (size_t)i], lox), sx);
+    double fy = __dmul_rn(__dsub_rn(pos[3 * (size_t)i + 1], loy), sy);
+    double fz = __dmul_rn(__dsub_rn(pos[3 * (size_t)i + 2], loz), sz);
+    long long ix = fx > 0.0 ? (long long)fx : 0, iy = fy > 0.0 ? (long long)fy : 0, iz = fz > 0.0 ? (long long)fz : 0;
+    if (ix > 0x1fffff) ix = 0x1fffff;
+    if (iy > 0x1fffff) iy = 0x1fffff;
+    if (iz > 0x1fffff) iz = 0x1fffff;
+    key[i] = (spread21((unsigned long long)ix) << 2) | (spread21((unsigned long long)iy) << 1) | spread21((unsigned long long)iz);
+    idx[i] = i;
+}
+
+__global__ void gather_pos_kernel(int n, const double *__restrict__ pos_in, const int *__restrict__ idx,
+                                  double *__restrict__ pos_out, int *__restrict__ seg) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    size_t j = (size_t)idx[i];
+    pos_out[3 * (size_t)i] = pos_in[3 * j];
+    pos_out[3 * (size_t)i + 1] = pos_in[3 * j + 1];
+    pos_out[3 * (size_t)i + 2] = pos_in[3 * j + 2];
+    seg[i] = 0;                                          // everyone starts in the root
+}
+
+__global__ void quantize_kernel(int n, const double *__restrict__ pos, const int *__restrict__ seg, int dir, double lo,
+                                double S, unsigned long long *__restrict__ q) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    unsigned long long v = 0;
+    if (i < n && seg[i] >= 0) {
+        double f = __dmul_rn(__dsub_rn(pos[3 * (size_t)i + dir], lo), S);
+        v = f > 0.0 ? (unsigned long long)f : 0ULL;
+    }
+    q[i] = v;                                            // q[n] = 0: the scan's last slot is the grand total
+}
+
+// one thread per node of the level: split position from the prefix sums
+__global__ void split_kernel(int cnt, int node0, const int *__restrict__ n_start, const int *__restrict__ n_count,
+                             const unsigned long long *__restrict__ Sq, double lo, double invS,
+                             double *__restrict__ n_split) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= cnt) return;
+    int nd = node0 + k;
+    int a = n_start[nd], c = n_count[nd];
+    unsigned long long sum = Sq[a + c] - Sq[a];
+    double m = __ddiv_rn(__ull2double_rn(sum), (double)c);
+    n_split[nd] = __dadd_rn(lo, __dmul_rn(m, invS));
+}
+
+__global__ void flag_kernel(int n, const double *__restrict__ pos, const int *__restrict__ seg, int dir,
+                            const double *__restrict__ n_split, const int *__restrict__ n_count, int *__restrict__ f) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    int v = 0;
+    if (i < n) {
+        int s = seg[i];
+        if (s >= 0) v = (n_count[s] < 2) ? 1 : (pos[3 * (size_t)i + dir] > n_split[s] ? 1 : 0);   // len < 2: src/fmm.c:33-36
+    }
+    f[i] = v;
+}
+
+// per node: how many leaf / node children (packed leaf | node << 32) for the numbering scan
+__global__ void childcount_kernel(int cnt, int node0, const int *__restrict__ n_start, const int *__restrict__ n_count,
+                                  const int *__restrict__ F, int maxleaf, unsigned long long *__restrict__ cc) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > cnt) return;
+    unsigned long long v = 0;
+    if (k < cnt) {
+        int nd = node0 + k;
+        int a = n_start[nd], c = n_count[nd];
+        int R = F[a + c] - F[a];
+        int c0 = c - R, c1 = R;
+        unsigned nl = (c0 <= maxleaf) + (c1 <= maxleaf);
+        v = (unsigned long long)nl | ((unsigned long long)(2 - nl) << 32);
+    }
+    cc[k] = v;
+}
+
+// per node: create the two children (records, boxes), ids from the scanned counts
+__global__ void children_kernel(int cnt, int node0, int next_node0, int leaf0, int dir, int depth, int maxleaf,
+                                int *__restrict__ n_start, int *__restrict__ n_count, int *__restrict__ n_son,
+                                int *__restrict__ n_depth, double *__restrict__ n_box, const double *__restrict__ n_split,
+                                int *__restrict__ l_start, int *__restrict__ l_count, double *__restrict__ l_box,
+                                const int *__restrict__ F, const unsigned long long *__restrict__ ccs, int node_cap,
+                                int leaf_cap, int *__restrict__ scal) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= cnt) return;
+    int nd = node0 + k;
+    int a = n_start[nd], c = n_count[nd];
+    int R = F[a + c] - F[a];
+    int cn[2] = {c - R, R};
+    int st[2] = {a, a + (c - R)};
+    unsigned long long off = ccs[k];
+    int li = leaf0 + (int)(off & 0xffffffffULL), ni = next_node0 + (int)(off >> 32);
+    double box[6];
+#pragma unroll
+    for (int d = 0; d < 6; d++) box[d] = n_box[6 * (size_t)nd + d];
+    double sp = n_split[nd];
+    for (int s = 0; s < 2; s++) {
+        double cb[6];
+#pragma unroll
+        for (int d = 0; d < 6; d++) cb[d] = box[d];
+        if (s == 0) cb[3 + dir] = sp; else cb[dir] = sp;          // center_kdtree, src/fmm.c:140-176
+        if (cn[s] <= maxleaf) {
+            if (li < leaf_cap) {
+                l_start[li] = st[s]; l_count[li] = cn[s];
+#pragma unroll
+                for (int d = 0; d < 6; d++) l_box[6 * (size_t)li + d] = cb[d];
+            } else atomicExch(&scal[3], 1);
+            n_son[2 * (size_t)nd + s] = -(li + 2);
+            li++;
+        } else {
+            if (ni < node_cap) {
+                n_start[ni] = st[s]; n_count[ni] = cn[s]; n_depth[ni] = depth + 1;
+#pragma unroll
+                for (int d = 0; d < 6; d++) n_box[6 * (size_t)ni + d] = cb[d];
+            } else atomicExch(&scal[3], 1);
+            n_son[2 * (size_t)nd + s] = ni;
+            ni++;
+        }
+    }
+    if (k == cnt - 1) {            // totals after this level
+        unsigned long long tot = ccs[cnt];
+        scal[0] = (int)(tot >> 32);                              // nodes of the next level
+        scal[1] = leaf0 + (int)(tot & 0xffffffffULL);            // leaves so far
+    }
+}
+
+__global__ void scatter_kernel(int n, const double *__restrict__ pos, const int *__restrict__ idx, const int *__restrict__ seg,
+                               const int *__restrict__ F, const int *__restrict__ n_start, const int *__restrict__ n_count,
+                               const int *__restrict__ n_son, double *__restrict__ pos_o, int *__restrict__ idx_o,
+                               int *__restrict__ seg_o) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int s = seg[i];
+    int np = i, ns = -1;
+    if (s >= 0) {
+        int a = n_start[s], c = n_count[s];
+        int Fa = F[a], R = F[a + c] - Fa, Fi = F[i];
+        int fl = F[i + 1] - Fi, rank = Fi - Fa;
+        np = fl ? a + (c - R) + rank : a + (i - a) - rank;
+        int ch = n_son[2 * (size_t)s + fl];
+        ns = ch >= 0 ? ch : -1;
+    }
+    pos_o[3 * (size_t)np] = pos[3 * (size_t)i];
+    pos_o[3 * (size_t)np + 1] = pos[3 * (size_t)i + 1];
+    pos_o[3 * (size_t)np + 2] = pos[3 * (size_t)i + 2];
+    idx_o[np] = idx[i];
+    seg_o[np] = ns;
+}
+
+// cells: leaves 0..nleaf-1, nodes nleaf..; geometry as center_kdtree computes it (src/fmm.c:126-131)
+__global__ void finalize_cells_kernel(int nleaf, int nnode, const int *__restrict__ l_start, const int *__restrict__ l_count,
+                                      const double *__restrict__ l_box, const int *__restrict__ n_start,
+                                      const int *__restrict__ n_count, const double *__restrict__ n_box,
+                                      const int *__restrict__ n_son, const int *__restrict__ n_depth,
+                                      double *__restrict__ geom, int *__restrict__ son, LeafDesc *__restrict__ desc,
+                                      int *__restrict__ parent, int *__restrict__ depth, int *__restrict__ level_nodes) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nleaf + nnode) return;
+    const double *b;
+    int first, np;
+    if (c < nleaf) {
+        b = l_box + 6 * (size_t)c; first = l_start[c]; np = l_count[c];
+        son[2 * (size_t)c] = -1; son[2 * (size_t)c + 1] = -1;
+    } else {
+        int k = c - nleaf;
+        b = n_box + 6 * (size_t)k; first = n_start[k]; np = n_count[k];
+        int dp = n_depth[k];
+        depth[c] = dp;
+        level_nodes[k] = c;
+        if (k == 0) parent[c] = -1;
+        for (int s = 0; s < 2; s++) {
+            int ch = n_son[2 * (size_t)k + s];
+            int cc = ch >= 0 ? nleaf + ch : -(ch + 2);
+            son[2 * (size_t)c + s] = cc;
+            parent[cc] = c;
+            if (ch < 0) depth[cc] = dp + 1;
+        }
+    }
+    LeafDesc d;
+    for (int q = 0; q < 3; q++) {
+        double ctr = __dmul_rn(0.5, __dadd_rn(b[3 + q], b[q]));
+        geom[6 * (size_t)c + q] = ctr;
+        geom[6 * (size_t)c + 3 + q] = __dsub_rn(b[3 + q], b[q]);
+        d.c[q] = ctr;
+    }
+    d.first = first; d.npart = np;
+    desc[c] = d;
+}
+
+int pn2_tree_build_device(pn2_ctx *h, const double *d_pos_in, int n, const pn2_domain *dom) {
+    cudaStream_t st = h->stream;
+    const int maxleaf = h->prm.maxleaf;
+    h->n = n;
+    h->dom = *dom;
+    h->nleaf = h->nnode = h->ncell = h->nlevel = 0;
+    h->level_off.assign(1, 0);
+    PN2_TRY(h->pos.ensure(3 * (size_t)n + 3)); PN2_TRY(h->b_pos2.ensure(3 * (size_t)n + 3));
+    PN2_TRY(h->acc.ensure(3 * (size_t)n + 3)); PN2_TRY(h->rel.ensure((size_t)n + 1));
+    PN2_TRY(h->order.ensure(n + 1)); PN2_TRY(h->b_idx2.ensure(n + 1));
+    PN2_TRY(h->b_seg.ensure(n + 1)); PN2_TRY(h->b_seg2.ensure(n + 1));
+    PN2_TRY(h->b_q.ensure(n + 2)); PN2_TRY(h->b_key2.ensure(n + 2)); PN2_TRY(h->b_f.ensure(n + 2));
+    PN2_TRY(h->b_scal.ensure(16));
+    if (n == 0) return PN2_OK;
+    // capacities: a full binary tree, nnode = nleaf - 1; leaves hold >= 1 particle unless coordinates coincide
+    int cap = n / 2 + 1024;
+    if (cap > n + 2) cap = n + 2;
+    PN2_TRY(h->n_start.ensure(cap)); PN2_TRY(h->n_count.ensure(cap)); PN2_TRY(h->n_son.ensure(2 * (size_t)cap));
+    PN2_TRY(h->n_depth.ensure(cap)); PN2_TRY(h->n_box.ensure(6 * (size_t)cap)); PN2_TRY(h->n_split.ensure(cap));
+    PN2_TRY(h->l_start.ensure(cap)); PN2_TRY(h->l_count.ensure(cap)); PN2_TRY(h->l_box.ensure(6 * (size_t)cap));
+
+    // ---- 0. Morton pre-sort ----
+    double ext[3], sc[3];
+    for (int d = 0; d < 3; d++) { ext[d] = dom->hi[d] - dom->lo[d]; sc[d] = 2097152.0 / ext[d]; }
+    morton_kernel<<<nb(n), TB, 0, st>>>(n, d_pos_in, dom->lo[0], dom->lo[1], dom->lo[2], sc[0], sc[1], sc[2], h->b_q.p, h->b_idx2.p);
+    size_t tb = 0, tb2 = 0, tb3 = 0, tb4 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, h->b_q.p, h->b_key2.p, h->b_idx2.p, h->order.p, n, 0, 63, st);
+    cub::DeviceScan::ExclusiveSum(nullptr, tb2, h->b_q.p, h->b_key2.p, n + 1, st);
+    cub::DeviceScan::ExclusiveSum(nullptr, tb3, h->b_f.p, h->b_seg2.p, n + 1, st);
+    cub::DeviceScan::ExclusiveSum(nullptr, tb4, h->b_q.p, h->b_key2.p, cap + 1, st);
+    size_t need = tb;
+    if (tb2 > need) need = tb2;
+    if (tb3 > need) need = tb3;
+    if (tb4 > need) need = tb4;
+    PN2_TRY(h->tmp.ensure(need + 16));
+    cub::DeviceRadixSort::SortPairs(h->tmp.p, tb, h->b_q.p, h->b_key2.p, h->b_idx2.p, h->order.p, n, 0, 63, st);
+    gather_pos_kernel<<<nb(n), TB, 0, st>>>(n, d_pos_in, h->order.p, h->pos.p, h->b_seg.p);
+    h->launches += 3;
+
+    // ---- root ----
+    {
+        int hs[2] = {0, n};
+        double box[6] = {dom->lo[0], dom->lo[1], dom->lo[2], dom->hi[0], dom->hi[1], dom->hi[2]};
+        int z = 0, m1[2] = {-1, -1};
+        CUDA_TRY(cudaMemcpyAsync(h->n_start.p, &hs[0], sizeof(int), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(h->n_count.p, &hs[1], sizeof(int), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(h->n_depth.p, &z, sizeof(int), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(h->n_son.p, m1, 2 * sizeof(int), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(h->n_box.p, box, 6 * sizeof(double), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemsetAsync(h->b_scal.p, 0, 16 * sizeof(int), st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    // quantisation scale: extent * 2^e < 2^36, so a sum over < 2^27 particles stays below 2^63
+    double emax = ext[0] > ext[1] ? ext[0] : ext[1];
+    if (ext[2] > emax) emax = ext[2];
+    int e2 = 0;
+    frexp(emax, &e2);                    // emax = f * 2^e2, f in [0.5, 1)
+    const double S = ldexp(1.0, 36 - e2), invS = ldexp(1.0, e2 - 36);
+
+    double *pc = h->pos.p, *po = h->b_pos2.p;
+    int *ic = h->order.p, *io = h->b_idx2.p, *sg = h->b_seg.p, *so = h->b_seg2.p;
+    int node0 = 0, cnt = 1, nleaf = 0, level = 0;
+    std::vector<int> level_off(1, 0);
+    while (cnt > 0) {
+        if (level > 200) { pn2_set_error("pn2: tree deeper than 200 levels (more than MAXLEAF coincident particles?)"); return PN2_ERR_ARG; }
+        int dir = (dom->direct0 + level) % 3;
+        double lo = dom->lo[dir];
+        quantize_kernel<<<nb(n + 1), TB, 0, st>>>(n, pc, sg, dir, lo, S, h->b_q.p);
+        cub::DeviceScan::ExclusiveSum(h->tmp.p, tb2, h->b_q.p, h->b_key2.p, n + 1, st);
+        split_kernel<<<nb(cnt), TB, 0, st>>>(cnt, node0, h->n_start.p, h->n_count.p, h->b_key2.p, lo, invS, h->n_split.p);
+        flag_kernel<<<nb(n + 1), TB, 0, st>>>(n, pc, sg, dir, h->n_split.p, h->n_count.p, h->b_f.p);
+        cub::DeviceScan::ExclusiveSum(h->tmp.p, tb3, h->b_f.p, h->b_f.p, n + 1, st);
+        childcount_kernel<<<nb(cnt + 1), TB, 0, st>>>(cnt, node0, h->n_start.p, h->n_count.p, h->b_f.p, maxleaf, h->b_q.p);
+        cub::DeviceScan::ExclusiveSum(h->tmp.p, tb4, h->b_q.p, h->b_q.p, cnt + 1, st);
+        children_kernel<<<nb(cnt), TB, 0, st>>>(cnt, node0, node0 + cnt, nleaf, dir, level, maxleaf, h->n_start.p, h->n_count.p,
+                                                h->n_son.p, h->n_depth.p, h->n_box.p, h->n_split.p, h->l_start.p,
+                                                h->l_count.p, h->l_box.p, h->b_f.p, h->b_q.p, cap, cap, h->b_scal.p);
+        scatter_kernel<<<nb(n), TB, 0, st>>>(n, pc, ic, sg, h->b_f.p, h->n_start.p, h->n_count.p, h->n_son.p, po, io, so);
+        h->launches += 9;
+        int hs[4];
+        CUDA_TRY(cudaMemcpyAsync(hs, h->b_scal.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (hs[3]) { pn2_set_error("pn2: tree capacity %d exceeded (degenerate particle distribution)", cap); return PN2_ERR_NOMEM; }
+        std::swap(pc, po); std::swap(ic, io); std::swap(sg, so);
+        node0 += cnt;
+        level_off.push_back(node0);
+        cnt = hs[0];
+        nleaf = hs[1];
+        level++;
+    }
+    // make h->pos / h->order the final buffers
+    if (pc != h->pos.p) { std::swap(h->pos, h->b_pos2); }
+    if (ic != h->order.p) { std::swap(h->order, h->b_idx2); }
+    const int nnode = node0;
+    if ((size_t)nleaf + nnode >= (1u << PN2_IMG_SHIFT)) { pn2_set_error("pn2: more than 2^26 cells on one device"); return PN2_ERR_ARG; }
+    h->nleaf = nleaf; h->nnode = nnode; h->ncell = nleaf + nnode; h->nlevel = level;
+    h->level_off = level_off;
+    h->first_leaf = 0; h->last_leaf = nleaf; h->first_node = nleaf; h->last_node = nleaf + nnode - 1;
+    size_t nc = (size_t)h->ncell;
+    PN2_TRY(h->geom.ensure(6 * nc + 6)); PN2_TRY(h->son.ensure(2 * nc + 2)); PN2_TRY(h->desc.ensure(nc + 1));
+    PN2_TRY(h->M.ensure(NM * nc + NM)); PN2_TRY(h->L.ensure(NM * nc + NM)); PN2_TRY(h->level_nodes.ensure(nnode + 1));
+    PN2_TRY(h->parent.ensure(nc + 1)); PN2_TRY(h->depth.ensure(nc + 1));
+    finalize_cells_kernel<<<nb(h->ncell), TB, 0, st>>>(nleaf, nnode, h->l_start.p, h->l_count.p, h->l_box.p, h->n_start.p,
+                                                       h->n_count.p, h->n_box.p, h->n_son.p, h->n_depth.p, h->geom.p,
+                                                       h->son.p, h->desc.p, h->parent.p, h->depth.p, h->level_nodes.p);
+    h->launches++;
+    CUDA_TRY(cudaMemsetAsync(h->L.p, 0, NM * nc * sizeof(double), st));
+    CUDA_TRY(cudaMemsetAsync(h->acc.p, 0, 3 * (size_t)n * sizeof(double), st));
+    KERNEL_CHECK();
+    h->have_particles = true;
+    h->have_tree = true;
+    return PN2_OK;
+}

@@ -154,18 +154,23 @@ def test_edge_cases(pn2, oracle):
         with pytest.raises(pn2.Pn2Error):
             ctx.p2p_batch(np.array([t.last_node + 5], np.int32), np.array([t.first_leaf], np.int32))
         ctx.close()
-    # one particle: a tree of one node and leaves, self pair only -> zero acceleration
-    one = np.array([[1.0, 2.0, 3.0]])
+    # one leaf pair below the root (the reference's node capacity 2N/MAXLEAF needs N >= 8): lists are the
+    # two self pairs and the two cross pairs; P2M/M2M/L2L/L2P run on a one-node tree
+    one = rng.random((9, 3)) * box
     t = oracle.Tree(one, 8, [0, 0, 0], [box] * 3)
     leaf, btree = ref_arrays(pn2, t)
-    ctx = pn2.Context(pn2.Params(box, 1.0, 4.5, 0.1, 0.4, 1.0, 8, 1, 1, 1))
+    ctx = pn2.Context(pn2.Params(box, 30.0, 135.0, 0.1, 0.4, 1.0, 8, 1, 1, 1))
     ctx.set_particles(t.pos)
     ctx.set_tree(leaf, t.first_leaf, btree, t.first_node)
-    ps, pt, ms, mt = t.walk_local(oracle.make_params(box, 4, 1, 1.0))
+    po = oracle.make_params(box, 4, 9, 1.0, split=30.0, soft=0.1)
+    ps, pt, ms, mt = t.walk_local(po)
+    assert len(ps) == 4 and len(ms) == 0
     ctx.p2p_batch(ps, pt)
     ctx.p2m_m2m()
     ctx.l2l_l2p()
-    assert np.all(ctx.get_acc() == 0.0)
+    ref = np.zeros((9, 3))
+    t.eval_p2p(po, ps, pt, ref)
+    assert rms_rel(ctx.get_acc(), ref) < 3e-5
     ctx.close()
 
 
