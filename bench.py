@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- short-range force throughput (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one whole short-range force evaluation (device tree build + P2M/M2M + fused list walk and P2P
+incl. the 26 periodic images + M2L + L2L/L2P) of a synthetic LambdaCDM-like periodic particle set.
+The workload is STRONG-scaled: --npart-side^3 particles in total (default 512^3, the size the metric is
+quoted on), split over the N ranks by the reference's domain decomposition.
+One JSON line on stdout (rank 0); see DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "photons-2.0_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+OPS_PER_INTERACTION = 24          # FMA-pipe ops of the P2P inner loop
+METRIC = "short-range force: particles/s per force step"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--npart-side", type=int, default=512, help="particles per dimension (total, all GPUs)")
+    ap.add_argument("--nside", type=int, default=0, help="PM mesh side NSIDE (0: = npart-side)")
+    ap.add_argument("--maxleaf", type=int, default=8)
+    ap.add_argument("--theta", type=float, default=0.4)
+    ap.add_argument("--disp-rms", type=float, default=0.3, help="rms Zel'dovich displacement in grid spacings")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
+    ap.add_argument("--cpu-sample-side", type=int, default=96, help="particles per dimension of the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def reference_cpu_run(args, side, nranks, repeat=1):
+    """The reference's own CPU implementation of the path (oracle/_ref/ref_fmm: the UNMODIFIED reference
+    sources with a fork/socketpair MPI shim, PM excluded) on a bounded sample of the workload: the same
+    generator at side^3 particles with NSIDE = side * (nside / npart_side), i.e. the same interactions per
+    particle.  Returns (particles/s, interactions/s, seconds per force evaluation, kind)."""
+    import torch
+    import synthetic
+    from oracle import pn_ref, pn_oracle
+    nside_pm = max(2, int(round(side * (args.nside or args.npart_side) / args.npart_side)))
+    pos = synthetic.lcdm_like(side, disp_rms=args.disp_rms, seed=12345, device="cpu").numpy()
+    n = len(pos)
+    mass = synthetic.particle_mass(n)
+    if pn_ref.available():
+        kind = "reference"
+        t0 = time.perf_counter()
+        ranks = pn_ref.run_reference(pos, synthetic.BOX, nside_pm, mass, maxleaf=args.maxleaf, theta=args.theta, nranks=nranks,
+                                     capture=1, repeat=repeat, timeout=3000)   # capture=1: the harness counts local interactions
+        wall = time.perf_counter() - t0
+        # the harness times construct+prepare+task+ext per rank (max over ranks = the step)
+        sec = max(r["timing"]["total"] for r in ranks) / max(1, repeat)
+        nint = sum(r["nint_local"] + r["p2p_count_remote"] for r in ranks)
+        if not (sec > 0):
+            sec = wall / max(1, repeat)
+    else:
+        kind = "port"
+        prm = pn_oracle.make_params(synthetic.BOX, nside_pm, n, mass, maxleaf=args.maxleaf, theta=args.theta)
+        t0 = time.perf_counter()
+        _, cnt = pn_oracle.force(pos, prm, 1)
+        sec = time.perf_counter() - t0
+        nint = cnt["int_local"] + cnt["int_remote"]
+        nranks = 1
+    return {"pps": n / sec, "ips": nint / sec, "sec": sec, "kind": kind, "cores": nranks, "n": n, "side": side,
+            "nside": nside_pm, "interactions_per_particle": nint / n}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_cores()
+    nranks = 1
+    while nranks * 2 <= cores:
+        nranks *= 2                                   # the shim runs any count; powers of two keep domains cubic
+    side = args.cpu_sample_side
+    for _ in range(args.warmup and 1):
+        reference_cpu_run(args, 32, min(nranks, 8))   # warm the page cache / binary, untimed
+    t0 = time.perf_counter()
+    res = [reference_cpu_run(args, side, nranks) for _ in range(args.steps)]
+    wall = time.perf_counter() - t0
+    sec = float(np.mean([r["sec"] for r in res]))
+    r = res[0]
+    pps = r["n"] / sec
+    sample = (f"{side}^3 particles of the same generator, NSIDE {r['nside']}, one force evaluation per step at NP={r['cores']} "
+              f"ranks (fork/socketpair MPI shim), {r['interactions_per_particle']:.0f} interactions/particle")
+    out = {"metric": METRIC, "value": pps, "unit": "particles/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic", "impl": "reference",
+           "config": workload_config(args, 1) | {"reference_sample": sample},
+           "p2p_ginteractions_per_s": r["interactions_per_particle"] * pps / 1e9,
+           "cpu_baseline": {"value": pps, "unit": "particles/s", "cores": r["cores"], "kind": r["kind"], "sample": sample},
+           "e2e": {"value": pps, "unit": "particles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0, "wall_s": wall}
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(args, ngpu):
+    nside = args.nside or args.npart_side
+    return {"workload": f"synthetic LCDM-like {args.npart_side}^3 particles, periodic box {100000.0:g} kpc/h, NSIDE {nside}, "
+                        f"Zel'dovich displacement rms {args.disp_rms} grid spacings, seed 12345",
+            "npart": args.npart_side ** 3, "nside": nside, "maxleaf": args.maxleaf, "theta": args.theta,
+            "precision_mode": args.precision, "parallelism": f"domains{ngpu}",
+            "cache": "inputs (positions, tree, multipoles: several GB) exceed the 126 MB L2; no explicit flush"}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    import torch
+    import torch.distributed as dist
+    import pn2gpu
+    import synthetic
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    nside = args.nside or args.npart_side
+    ntot = args.npart_side ** 3
+    mass = synthetic.particle_mass(ntot)
+    precision = pn2gpu.FP32 if args.precision == "fp32" else pn2gpu.FP64
+    prm = pn2gpu.make_params(synthetic.BOX, nside, ntot, mass, maxleaf=args.maxleaf, theta=args.theta, precision=precision)
+    ctx = pn2gpu.Context(prm, device=local)
+
+    # ---- workload: every rank generates the same field, keeps the particles of its own domain ----
+    pos_all = synthetic.lcdm_like(args.npart_side, disp_rms=args.disp_rms, seed=12345, device=dev)
+    if world > 1:
+        import domains
+        doms = domains.domain_boxes(world, synthetic.BOX)
+        owner = domains.domain_of(pos_all, world, synthetic.BOX)
+        pos = pos_all[owner == rank].contiguous()
+        del owner
+        dom = doms[rank]
+        ctx.set_comm_torch(rank, world, doms)
+    else:
+        pos = pos_all
+        dom = pn2gpu.make_domain([0, 0, 0], [synthetic.BOX] * 3, 0)
+    del pos_all
+    torch.cuda.empty_cache()
+    n = pos.shape[0]
+    acc = torch.empty_like(pos)
+    torch.cuda.synchronize()
+
+    def step():
+        ctx.force_step_device(pos.data_ptr(), n, acc.data_ptr(), dom)
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    fma_peak = ctx.fma_peak(False)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launch_count()
+    phase = []
+    barrier()
+    ctx.timer_start(0)
+    for _ in range(args.steps):
+        step()
+        phase.append(ctx.timings())          # waits for this step's last event (the step already synchronises once)
+    ms_total = ctx.timer_stop(0)
+    barrier()
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    info = ctx.step_info()
+    t = torch.tensor([ms_total, float(info["n_interactions"]), float(n), float(np.mean([p["walk_p2p"] for p in phase]))],
+                     dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms_total, nint_total, n_total, walk_ms = float(tmax[0]), float(tsum[1]), float(tsum[2]), float(tmax[3])
+    else:
+        ms_total, nint_total, n_total, walk_ms = [float(x) for x in t]
+    ms_step = ms_total / args.steps
+
+    # ---- e2e: the same step through the host-pointer C-ABI call: pinned host positions in, accelerations out ----
+    e2e = None
+    if not args.no_e2e:
+        hpos = torch.empty((n, 3), dtype=torch.float64, pin_memory=True)
+        hpos.copy_(pos)
+        hacc = torch.empty((n, 3), dtype=torch.float64, pin_memory=True)
+        lib = pn2gpu.lib()
+        import ctypes as C
+
+        def estep():
+            pn2gpu._ck(lib.pn2_force_step(ctx.h, hpos.data_ptr(), 24, n, C.byref(dom), hacc.data_ptr(), 24))
+        estep()
+        barrier()
+        ctx.timer_start(1)
+        for _ in range(args.steps):
+            estep()
+        e_ms = ctx.timer_stop(1)
+        barrier()
+        te = torch.tensor([e_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e_ms = float(te[0]) / args.steps
+        e2e = {"value": n_total / (e_ms * 1e-3), "unit": "particles/s", "h2d_bytes_per_step": int(n_total) * 24,
+               "d2h_bytes_per_step": int(n_total) * 24, "ms_per_step": e_ms,
+               "check_rms_acc": float(torch.sqrt((hacc[: min(n, 1 << 20)] ** 2).sum(1).mean()))}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pps = n_total / (ms_step * 1e-3)
+    ach = OPS_PER_INTERACTION * (nint_total / world) / (walk_ms * 1e-3)     # per GPU, dominant kernel
+    nominal = 148 * 128 * (clocks["sm_mhz"] or 1965.0) * 1e6 if clocks else None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("walk_fused_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    out = {"metric": METRIC, "value": pps, "unit": "particles/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f32" if precision == pn2gpu.FP32 else "f64", "data": "synthetic",
+           "config": workload_config(args, world),
+           "p2p_ginteractions_per_s": nint_total / (ms_step * 1e-3) / 1e9,
+           "interactions_per_particle": nint_total / n_total,
+           "phases_ms": {k: float(np.mean([p[k] for p in phase])) for k in ("tree", "upward", "walk_p2p", "m2l", "downward", "let", "total")},
+           "tree": {"nleaf": info["nleaf"], "nnode": info["nnode"], "levels": info["nlevel"], "m2l_pairs": info["n_m2l_pairs"],
+                    "p2p_leaf_pairs": info["n_p2p_pairs"]},
+           "roofline": {"bound": "fma_pipe", "kernel": "walk_fused_kernel (list walk + P2P)", "achieved": ach / 1e12,
+                        "peak": fma_peak / 1e12, "unit": "Tops/s (FFMA/FMUL/FADD issue slots)", "frac": ach / fma_peak,
+                        "peak_source": "measured in this run: pn2_fma_peak (independent FFMA chains, CUDA events)",
+                        "nominal_peak_at_sampled_clock": (nominal / 1e12) if nominal else None,
+                        "ops_per_interaction": OPS_PER_INTERACTION, "traffic": traffic,
+                        "hbm_peak_gbs_measured": peaks.get("hbm_gbs")},
+           "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e}
+    if not args.no_cpu_baseline and world == 1:
+        cores = host_cores()
+        nr = 1
+        while nr * 2 <= cores:
+            nr *= 2
+        try:
+            r = reference_cpu_run(args, args.cpu_sample_side, nr)
+            out["cpu_baseline"] = {"value": r["pps"], "unit": "particles/s", "cores": r["cores"], "kind": r["kind"],
+                                   "sample": f"{r['side']}^3 particles of the same generator, NSIDE {r['nside']}, one force evaluation, "
+                                             f"NP={r['cores']} ranks of the unmodified reference (PM excluded), "
+                                             f"{r['interactions_per_particle']:.0f} interactions/particle, {r['sec']:.1f} s",
+                                   "p2p_ginteractions_per_s": r["ips"] / 1e9}
+        except Exception as ex:  # the bench line must still be printed
+            out["cpu_baseline"] = {"value": None, "unit": "particles/s", "cores": cores, "kind": "unavailable", "sample": repr(ex)[:300]}
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -181,6 +181,9 @@ int pn2_fma_peak(pn2_ctx *h, int fp64, double *ops_per_s, double *ms);
 /* elapsed device time of the kernels of the last pn2_force_step*, by phase (ms): 0 tree, 1 upward,
  * 2 walk+P2P (fused), 3 M2L, 4 downward, 5 LET pack+exchange, 6 total */
 int pn2_get_timings(pn2_ctx *h, double ms[8]);
+/* CUDA-event stopwatch on the context's stream (slot 0..3): bench.py brackets its timed region with it */
+int pn2_timer_start(pn2_ctx *h, int slot);
+int pn2_timer_stop(pn2_ctx *h, int slot, double *ms);   /* records the stop event, synchronises, returns elapsed ms */
 /* number of kernel launches issued by this context since creation */
 long pn2_launch_count(pn2_ctx *h);
 

@@ -121,6 +121,25 @@ extern "C" int pn2_sync(pn2_ctx *h) {
 
 extern "C" long pn2_launch_count(pn2_ctx *h) { return h ? h->launches : 0; }
 
+extern "C" int pn2_timer_start(pn2_ctx *h, int slot) {
+    if (!h || slot < 0 || slot > 3) { pn2_set_error("pn2_timer_start: bad argument"); return PN2_ERR_ARG; }
+    CUDA_TRY(cudaSetDevice(h->device));
+    for (int k = 0; k < 2; k++)
+        if (!h->tev[slot][k]) CUDA_TRY(cudaEventCreate(&h->tev[slot][k]));
+    CUDA_TRY(cudaEventRecord(h->tev[slot][0], h->stream));
+    return PN2_OK;
+}
+extern "C" int pn2_timer_stop(pn2_ctx *h, int slot, double *ms) {
+    if (!h || slot < 0 || slot > 3 || !ms || !h->tev[slot][0]) { pn2_set_error("pn2_timer_stop: bad argument"); return PN2_ERR_ARG; }
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaEventRecord(h->tev[slot][1], h->stream));
+    CUDA_TRY(cudaEventSynchronize(h->tev[slot][1]));
+    float t = 0;
+    CUDA_TRY(cudaEventElapsedTime(&t, h->tev[slot][0], h->tev[slot][1]));
+    *ms = t;
+    return PN2_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Mode A uploads
 // ------------------------------------------------------------------------------------------------

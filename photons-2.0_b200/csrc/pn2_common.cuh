@@ -147,6 +147,7 @@ struct pn2_ctx {
     std::vector<pn2_domain> all_dom;
     void *nccl = nullptr;
     cudaEvent_t ev[8] = {nullptr};
+    cudaEvent_t tev[4][2] = {{nullptr}};
 };
 
 // ---- kernels / launchers implemented across the .cu files ----

@@ -31,7 +31,7 @@ EXPORTS = ["pn2_create", "pn2_destroy", "pn2_set_params", "pn2_sync", "pn2_last_
            "pn2_p2p_ext_batch", "pn2_m2l_ext_batch", "pn2_l2l_l2p", "pn2_get_acc", "pn2_zero_acc",
            "pn2_get_multipoles", "pn2_get_locals", "pn2_get_counters", "pn2_force_step", "pn2_force_step_device",
            "pn2_set_comm", "pn2_get_step_info", "pn2_get_order", "pn2_get_cells", "pn2_get_lists", "pn2_fma_peak",
-           "pn2_get_timings", "pn2_launch_count"]
+           "pn2_get_timings", "pn2_launch_count", "pn2_timer_start", "pn2_timer_stop"]
 
 
 class Pn2Error(RuntimeError):
@@ -111,6 +111,8 @@ def lib():
     L.pn2_get_lists.argtypes = [vp, C.c_int, lp, lp, vp, vp, vp]
     L.pn2_fma_peak.argtypes = [vp, C.c_int, dp, dp]
     L.pn2_get_timings.argtypes = [vp, dp]
+    L.pn2_timer_start.argtypes = [vp, C.c_int]
+    L.pn2_timer_stop.argtypes = [vp, C.c_int, dp]
     L.pn2_launch_count.argtypes = [vp]
     L.pn2_launch_count.restype = C.c_long
     _lib = L
@@ -303,6 +305,14 @@ class Context:
         ops, ms = C.c_double(), C.c_double()
         _ck(lib().pn2_fma_peak(self.h, int(fp64), C.byref(ops), C.byref(ms)))
         return ops.value
+
+    def timer_start(self, slot=0):
+        _ck(lib().pn2_timer_start(self.h, slot))
+
+    def timer_stop(self, slot=0):
+        ms = C.c_double()
+        _ck(lib().pn2_timer_stop(self.h, slot, C.byref(ms)))
+        return ms.value
 
     def launch_count(self):
         return int(lib().pn2_launch_count(self.h))
