@@ -316,9 +316,10 @@ def main():
            "config": workload_config(args, world),
            "p2p_ginteractions_per_s": nint_total / (ms_step * 1e-3) / 1e9,
            "interactions_per_particle": nint_total / n_total,
-           "phases_ms": {k: float(np.mean([p[k] for p in phase])) for k in ("tree", "upward", "walk_p2p", "m2l", "downward", "let", "total")},
+           "phases_ms": {k: float(np.mean([p[k] for p in phase])) for k in ("tree", "upward", "frontier", "walk_p2p", "m2l", "downward", "let", "total")},
            "tree": {"nleaf": info["nleaf"], "nnode": info["nnode"], "levels": info["nlevel"], "m2l_pairs": info["n_m2l_pairs"],
-                    "p2p_leaf_pairs": info["n_p2p_pairs"]},
+                    "p2p_leaf_pairs": info["n_p2p_pairs"], "walk_visits": info["n_walk_visits"],
+                    "frontier_bytes": info["frontier_bytes"]},
            "roofline": {"bound": "fma_pipe", "kernel": "walk_fused_kernel (list walk + P2P)", "achieved": ach / 1e12,
                         "peak": fma_peak / 1e12, "unit": "Tops/s (FFMA/FMUL/FADD issue slots)", "frac": ach / fma_peak,
                         "peak_source": "measured in this run: pn2_fma_peak (independent FFMA chains, CUDA events)",

@@ -160,6 +160,8 @@ typedef struct {
     int64_t n_m2l_pairs;
     int64_t n_interactions;     /* ordered particle pairs (self terms excluded) */
     int64_t n_let_nodes, n_let_bodies;
+    int64_t n_walk_visits;      /* (sink, source) cell pairs examined by the list builder */
+    int64_t frontier_bytes;     /* size of the per-sink-node frontier lists */
 } pn2_step_info;
 int pn2_get_step_info(pn2_ctx *h, pn2_step_info *info);
 /* particle permutation (order[k] = caller index of the k-th particle in tree order) */
@@ -179,7 +181,7 @@ int pn2_get_lists(pn2_ctx *h, int kind /* 0 p2p, 1 m2l */, long *nseg, long *nsr
  * CUDA events on this device; the denominator of the FMA-pipe roofline. */
 int pn2_fma_peak(pn2_ctx *h, int fp64, double *ops_per_s, double *ms);
 /* elapsed device time of the kernels of the last pn2_force_step*, by phase (ms): 0 tree, 1 upward,
- * 2 walk+P2P (fused), 3 M2L, 4 downward, 5 LET pack+exchange, 6 total */
+ * 2 leaf walk + P2P (fused kernel), 3 M2L, 4 downward, 5 LET pack+exchange, 6 total, 7 frontier pass (lists by sink node) */
 int pn2_get_timings(pn2_ctx *h, double ms[8]);
 /* CUDA-event stopwatch on the context's stream (slot 0..3): bench.py brackets its timed region with it */
 int pn2_timer_start(pn2_ctx *h, int slot);

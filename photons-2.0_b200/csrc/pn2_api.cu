@@ -153,8 +153,10 @@ extern "C" int pn2_set_particles(pn2_ctx *h, const double *pos, size_t stride_by
     PN2_TRY(h->pos.ensure(3 * (size_t)n + 3));
     PN2_TRY(h->acc.ensure(3 * (size_t)n + 3));
     PN2_TRY(h->rel.ensure((size_t)n + 1));
-    if (n > 0)
-        CUDA_TRY(cudaMemcpy2DAsync(h->pos.p, 24, pos, stride_bytes, 24, n, cudaMemcpyHostToDevice, h->stream));
+    if (n > 0) {
+        if (stride_bytes == 24) CUDA_TRY(cudaMemcpyAsync(h->pos.p, pos, 24 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+        else CUDA_TRY(cudaMemcpy2DAsync(h->pos.p, 24, pos, stride_bytes, 24, n, cudaMemcpyHostToDevice, h->stream));
+    }
     CUDA_TRY(cudaMemsetAsync(h->acc.p, 0, 3 * (size_t)n * sizeof(double), h->stream));
     CUDA_TRY(cudaMemsetAsync(h->counters.p, 0, 8 * sizeof(unsigned long long), h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));

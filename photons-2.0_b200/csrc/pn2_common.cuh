@@ -132,6 +132,9 @@ struct pn2_ctx {
     DBuf<double> n_box, n_split, l_box;                              // [cap][6] lo, hi
     DBuf<unsigned long long> b_cnt;  // per-level child counts (leaf | node << 32) and scan
     DBuf<int> b_scal;                // device scalars
+    DBuf<unsigned> spans;            // O(im) span lists of the frontier pass (16-byte units)
+    unsigned long long span_cap16 = 0, span_used16 = 0, walk_visits = 0;
+    DBuf<unsigned> o_head;           // [ncell]
     DBuf<unsigned> m2l_pairs;        // [cap][2] (sink cell, src cell | image << 26), appended by the walk
     size_t m2l_cap = 0;
     DBuf<long> lst_off;              // dump mode: per-leaf offsets
@@ -162,4 +165,5 @@ void pn2_modeb_release(pn2_ctx *h);
 int pn2_csr_from_device_pairs(pn2_ctx *h, int *tcell, unsigned *scell, long n, CsrList *out);
 int pn2_tree_build_device(pn2_ctx *h, const double *d_pos_in, int n, const pn2_domain *dom);
 int pn2_walk_fused(pn2_ctx *h, int dump);
+int pn2_walk_frontiers(pn2_ctx *h);
 void pn2_init_consts(pn2_ctx *h);

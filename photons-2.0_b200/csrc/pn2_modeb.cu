@@ -10,7 +10,7 @@ void pn2_modeb_release(pn2_ctx *h) {
     h->b_seg.release(); h->b_seg2.release(); h->b_q.release(); h->b_key2.release(); h->b_f.release();
     h->n_start.release(); h->n_count.release(); h->n_son.release(); h->n_depth.release(); h->l_start.release();
     h->l_count.release(); h->n_box.release(); h->n_split.release(); h->l_box.release(); h->b_cnt.release();
-    h->b_scal.release(); h->m2l_pairs.release(); h->lst_off.release(); h->lst_src.release(); h->lst_sink.release();
+    h->b_scal.release(); h->m2l_pairs.release(); h->spans.release(); h->o_head.release(); h->lst_off.release(); h->lst_src.release(); h->lst_sink.release();
     for (int i = 0; i < 8; i++) if (h->ev[i]) { cudaEventDestroy(h->ev[i]); h->ev[i] = nullptr; }
 }
 
@@ -60,22 +60,47 @@ extern "C" int pn2_force_step_device(pn2_ctx *h, const double *d_pos, int n, con
         PN2_TRY(h->m2l_pairs.ensure(2 * cap));
         h->m2l_cap = cap;
     }
-    unsigned long long cnt[4];
+    unsigned long long cnt[8];
+    PN2_TRY(h->o_head.ensure((size_t)h->ncell + 1));
+    if (h->span_cap16 < 1024 + 6ULL * (unsigned long long)n) {
+        h->span_cap16 = 1024 + 6ULL * (unsigned long long)n;          // 96 B per particle to start with; grown on demand
+        h->spans.release();
+        PN2_TRY(h->spans.ensure(4 * (size_t)h->span_cap16));
+    }
     for (int attempt = 0;; attempt++) {
         CUDA_TRY(cudaMemsetAsync(h->counters.p, 0, 8 * sizeof(unsigned long long), st));
+        const unsigned long long one = 1;                              // span unit 0 is reserved (0 = empty list)
+        CUDA_TRY(cudaMemcpyAsync(h->counters.p + 6, &one, sizeof one, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemsetAsync(h->o_head.p, 0, ((size_t)h->ncell + 1) * sizeof(unsigned), st));
+        PN2_TRY(pn2_walk_frontiers(h));
+        if (attempt == 0) CUDA_TRY(cudaEventRecord(h->ev[6], st));
         PN2_TRY(pn2_walk_fused(h, 0));
         CUDA_TRY(cudaMemcpyAsync(cnt, h->counters.p, sizeof cnt, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
-        if (cnt[3]) { pn2_set_error("pn2: walk stack overflow (pathological particle distribution)"); return PN2_ERR_NOMEM; }
-        if (cnt[1] <= h->m2l_cap) break;
-        if (attempt >= 2) { pn2_set_error("pn2: M2L list does not fit"); return PN2_ERR_NOMEM; }
-        // the M2L pair buffer was too small: grow it and redo the walk from clean accelerations
-        size_t cap = (size_t)cnt[1] + (size_t)cnt[1] / 4 + 1024;
-        h->m2l_pairs.release();
-        PN2_TRY(h->m2l_pairs.ensure(2 * cap));
-        h->m2l_cap = cap;
+        if (cnt[3] & 1) { pn2_set_error("pn2: walk stack overflow (pathological particle distribution)"); return PN2_ERR_NOMEM; }
+        bool redo = false;
+        if (cnt[3] & 2) {                                              // span buffer too small
+            unsigned long long want = cnt[6] + cnt[6] / 4 + 1024;
+            if (want >= (1ULL << 32)) { pn2_set_error("pn2: frontier lists exceed 64 GB"); return PN2_ERR_NOMEM; }
+            h->span_cap16 = want;
+            h->spans.release();
+            PN2_TRY(h->spans.ensure(4 * (size_t)h->span_cap16));
+            redo = true;
+        }
+        if (cnt[1] > h->m2l_cap) {                                     // M2L pair buffer too small
+            size_t cap = (size_t)cnt[1] + (size_t)cnt[1] / 4 + 1024;
+            h->m2l_pairs.release();
+            PN2_TRY(h->m2l_pairs.ensure(2 * cap));
+            h->m2l_cap = cap;
+            redo = true;
+        }
+        if (!redo) break;
+        if (attempt >= 3) { pn2_set_error("pn2: interaction lists do not fit"); return PN2_ERR_NOMEM; }
         CUDA_TRY(cudaMemsetAsync(h->acc.p, 0, 3 * (size_t)n * sizeof(double), st));
     }
+    h->span_used16 = cnt[6];
+    h->walk_visits = cnt[4];
+    h->info.n_walk_visits = (int64_t)cnt[4]; h->info.frontier_bytes = (int64_t)(16 * cnt[6]);
     h->info.n_interactions = (int64_t)cnt[0]; h->info.n_m2l_pairs = (int64_t)cnt[1]; h->info.n_p2p_pairs = (int64_t)cnt[2];
     CUDA_TRY(cudaEventRecord(h->ev[3], st));
     // M2L
@@ -103,9 +128,15 @@ extern "C" int pn2_force_step(pn2_ctx *h, const double *pos, size_t pos_stride, 
     CUDA_TRY(cudaSetDevice(h->device));
     static thread_local DBuf<double> in, out;
     PN2_TRY(in.ensure(3 * (size_t)n + 3)); PN2_TRY(out.ensure(3 * (size_t)n + 3));
-    if (n > 0) CUDA_TRY(cudaMemcpy2DAsync(in.p, 24, pos, pos_stride, 24, n, cudaMemcpyHostToDevice, h->stream));
+    if (n > 0) {
+        if (pos_stride == 24) CUDA_TRY(cudaMemcpyAsync(in.p, pos, 24 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+        else CUDA_TRY(cudaMemcpy2DAsync(in.p, 24, pos, pos_stride, 24, n, cudaMemcpyHostToDevice, h->stream));
+    }
     PN2_TRY(pn2_force_step_device(h, in.p, n, dom, out.p));
-    if (n > 0) CUDA_TRY(cudaMemcpy2DAsync(acc, acc_stride, out.p, 24, 24, n, cudaMemcpyDeviceToHost, h->stream));
+    if (n > 0) {
+        if (acc_stride == 24) CUDA_TRY(cudaMemcpyAsync(acc, out.p, 24 * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+        else CUDA_TRY(cudaMemcpy2DAsync(acc, acc_stride, out.p, 24, 24, n, cudaMemcpyDeviceToHost, h->stream));
+    }
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return PN2_OK;
 }
@@ -211,12 +242,13 @@ extern "C" int pn2_get_timings(pn2_ctx *h, double ms[8]) {
     for (int i = 0; i < 8; i++) ms[i] = 0.0;
     if (h->n == 0) return PN2_OK;
     CUDA_TRY(cudaEventSynchronize(h->ev[5]));
-    for (int i = 0; i < 5; i++) {
-        float t = 0;
-        CUDA_TRY(cudaEventElapsedTime(&t, h->ev[i], h->ev[i + 1]));
-        ms[i] = t;
-    }
     float t = 0;
+    CUDA_TRY(cudaEventElapsedTime(&t, h->ev[0], h->ev[1])); ms[0] = t;     // tree
+    CUDA_TRY(cudaEventElapsedTime(&t, h->ev[1], h->ev[2])); ms[1] = t;     // upward
+    CUDA_TRY(cudaEventElapsedTime(&t, h->ev[2], h->ev[6])); ms[7] = t;     // frontier pass (lists by sink node)
+    CUDA_TRY(cudaEventElapsedTime(&t, h->ev[6], h->ev[3])); ms[2] = t;     // fused leaf walk + P2P
+    CUDA_TRY(cudaEventElapsedTime(&t, h->ev[3], h->ev[4])); ms[3] = t;     // M2L
+    CUDA_TRY(cudaEventElapsedTime(&t, h->ev[4], h->ev[5])); ms[4] = t;     // downward
     CUDA_TRY(cudaEventElapsedTime(&t, h->ev[0], h->ev[5]));
     ms[6] = t;
     return PN2_OK;

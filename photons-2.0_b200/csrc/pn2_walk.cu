@@ -1,28 +1,31 @@
-// pn2_walk.cu -- Mode B: interaction-list construction fused with the P2P evaluation.
+// pn2_walk.cu -- Mode B: interaction-list construction on the device, fused with the P2P evaluation.
 //
-// One warp owns one sink leaf l.  It replays the reference's dual-tree walk (walk_task_p2p /
-// walk_task_m2l, src/fmm.c:406-712; remote version walk_task_*_ext, src/remotes.c:213-552) RESTRICTED to
-// sink-side cells on the path root -> l: whenever the reference would open the sink side, only the child
-// that contains l is followed.  Every decision is taken on the same (im, jm) pair with the same
-// acceptance() arithmetic (src/fmm.c:267-326, FP64, same expression order, no FMA contraction: this file
-// is compiled with -fmad=false), so the set of source leaves found for l is exactly the set of
-// (source, l) pairs the reference's walk emits.  An M2L pair (jm -> im) is met by every leaf below im;
-// it is emitted once, by the leaf that is the left-most descendant of im.
+// The reference builds its lists with a recursive dual-tree walk (walk_task_p2p / walk_task_m2l,
+// src/fmm.c:406-712; against received trees walk_task_*_ext, src/remotes.c:213-552).  Every call
+// walk(im, jm) decides from the PAIR alone (acceptance(), src/fmm.c:267-326) whether to emit, drop,
+// open the sink side im or open the source side jm.  The same traversal is organised here BY SINK CELL:
 //
-// Periodic images (src/fmm.c:1028-1045) and, on one rank, the self-exchange of 26 displaced pruned
-// trees are walked in place: image k is the local tree displaced by shift[k]; the sender-side pruning
-// of prepare_sendtree2 (src/remotes.c:97-158) is evaluated on the fly for the node being visited.
+//   F(im) = the set of sources jm for which the reference calls walk(im, jm)   ("frontier" of im)
+//   F(root) = {root} and, with periodic images, the 26 displaced copies of the root (src/fmm.c:1028-1045).
+//   Processing F(im) with the reference's rules gives  M2L pairs (jm -> im), dropped pairs, sources that
+//   re-enter F(im) (source side opened) and the list O(im) of sources handed to BOTH sons (sink side
+//   opened): F(son) = O(im).
 //
-// 32 (im, jm) pairs are popped per iteration from a per-warp stack in shared memory (one per lane); the
-// source leaves found go to a small queue which the same warp drains through the staged P2P pipeline of
-// pn2_p2p.cuh.  Nothing is written to HBM except accelerations (and the rare M2L pairs).
+// Pass 1 (frontier_node_kernel, one launch per tree level, one warp per sink node) walks the levels top
+// down and stores O(im) in a bump-allocated span list.  Pass 2 (walk_fused_kernel, one warp per sink
+// leaf) streams F(leaf) = O(parent), resolves it to source leaves and feeds them straight into the staged
+// P2P pipeline of pn2_p2p.cuh -- the P2P lists never exist in HBM.  Every pair (im, jm) is visited exactly
+// once, as in the reference; decisions use the reference's FP64 expressions in the same order (this file
+// is compiled with -fmad=false), so the lists are the reference's lists, bit for bit.
+//
+// Periodic images / self-exchange: image k is the local tree displaced by shift[k]; the sender-side
+// pruning of prepare_sendtree2 (src/remotes.c:97-158) is evaluated on the fly for the visited node.
 #include "pn2_p2p.cuh"
 
 #define WALK_WARPS 4
-#define STACK_CAP 768
-#define STACK_SOFT 640
+#define STACK_CAP 512
 #define SRCQ_CAP 64
-#define MAX_DEPTH 64
+#define OBUF_CAP 256              // per-warp staging of O(im) before it is flushed to a span
 
 struct WalkArgs {
     int nleaf, ncell, root;
@@ -30,19 +33,25 @@ struct WalkArgs {
     const int *son;
     const LeafDesc *desc;
     const int *parent;
-    const int *depth;
     const float4 *rel;
     const double *pos;
     double *acc;
     double cutoff, theta;
     int longshort, nimg, maxleaf;
     double tc[3], tw[3];               // this rank's domain box (pruning target for image trees)
+    // span lists: 16-byte units; span = {count, next, 0, 0} + entries
+    unsigned *spans;
+    unsigned long long span_cap16;     // capacity in 16-byte units
+    unsigned long long *span_top16;    // bump pointer
+    unsigned *o_head;                  // [ncell] first span of O(cell), 0 = empty
     unsigned *m2l_t, *m2l_s;
     unsigned long long m2l_cap;
-    unsigned long long *counters;      // [0] interactions, [1] m2l pairs, [2] p2p leaf pairs, [3] error flags
+    unsigned long long *counters;      // [0] interactions, [1] m2l pairs, [2] p2p leaf pairs, [3] error flags, [4] visits
     long *lst_off;                     // dump mode
     unsigned *lst_src;
     int pass, emit_m2l;
+    const int *work;                   // node kernel: cells of this level
+    int nwork;
 };
 
 // acceptance(), src/fmm.c:267-326: 0 open, 1 accept, -1 drop
@@ -88,46 +97,204 @@ __device__ __forceinline__ int pruned_dev(const double *c, const double *w, cons
     return 0;
 }
 
+__device__ __forceinline__ void load_geom(const double *geom, int cell, double c[3], double w[3]) {
+    const double2 *g = reinterpret_cast<const double2 *>(geom + 6 * (size_t)cell);     // 48-byte records, 16-byte aligned
+    double2 a = g[0], b = g[1], d = g[2];
+    c[0] = a.x; c[1] = a.y; c[2] = b.x; w[0] = b.y; w[1] = d.x; w[2] = d.y;
+}
+
+// streams the entries of a span list, 32 at a time
+struct SpanReader {
+    const unsigned *spans;
+    unsigned cur;       // current span (16-byte units), 0 = exhausted
+    unsigned cnt, pos;  // entries in the current span / consumed
+    __device__ void init(const unsigned *s, unsigned head) {
+        spans = s; cur = head; cnt = 0; pos = 0;
+        if (cur) cnt = spans[4 * (size_t)cur];
+    }
+    __device__ bool more() const { return cur != 0; }
+    // warp-uniform: returns the number of entries fetched (<= 32); lane i < n gets its entry in e
+    __device__ int fetch(int lane, unsigned &e) {
+        while (cur && pos >= cnt) {              // next span
+            cur = spans[4 * (size_t)cur + 1];
+            pos = 0;
+            cnt = cur ? spans[4 * (size_t)cur] : 0;
+        }
+        if (!cur) return 0;
+        int n = (int)(cnt - pos);
+        if (n > 32) n = 32;
+        if (lane < n) e = spans[4 * (size_t)cur + 4 + pos + lane];
+        pos += n;
+        return n;
+    }
+};
+
+// M2L pairs -> global list (warp-aggregated append)
+__device__ __forceinline__ void emit_m2l_pairs(const WalkArgs &a, int lane, unsigned lt_mask, int emit, unsigned snk, unsigned src) {
+    const unsigned mm = __ballot_sync(0xffffffffu, emit);
+    if (mm && a.emit_m2l) {
+        unsigned long long basei = 0;
+        if (lane == 0) basei = atomicAdd(&a.counters[1], (unsigned long long)__popc(mm));
+        basei = __shfl_sync(0xffffffffu, basei, 0);
+        if (emit) {
+            unsigned long long at = basei + __popc(mm & lt_mask);
+            if (at < a.m2l_cap) { a.m2l_t[at] = snk; a.m2l_s[at] = src; }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pass 1: one warp per sink NODE of one level: F(im) -> M2L pairs + O(im)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(WALK_WARPS * 32) frontier_node_kernel(WalkArgs a, P2PConst pc) {
+    __shared__ unsigned s_stack[WALK_WARPS][STACK_CAP];
+    __shared__ unsigned s_obuf[WALK_WARPS][OBUF_CAP];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int wk = blockIdx.x * WALK_WARPS + wib;
+    if (wk >= a.nwork) return;
+    const int im = a.work[wk];
+    const unsigned lt_mask = (1u << lane) - 1u;
+    unsigned *stack = s_stack[wib], *obuf = s_obuf[wib];
+
+    double ci[3], wi[3];
+    load_geom(a.geom, im, ci, wi);
+    const double swi = wi[0] + wi[1] + wi[2];
+
+    SpanReader rd;
+    if (im == a.root) {
+        rd.init(a.spans, 0);
+        if (lane < a.nimg) stack[lane] = (unsigned)a.root | ((unsigned)lane << PN2_IMG_SHIFT);
+    } else {
+        rd.init(a.spans, a.o_head[a.parent[im]]);
+    }
+    int ssize = (im == a.root) ? a.nimg : 0;
+    __syncwarp();
+
+    int osize = 0;
+    unsigned first_span = 0, prev_span = 0;
+    unsigned long long visits = 0;
+    int err = 0;
+    auto flush = [&]() {                     // obuf[0..osize) -> a new span
+        if (osize == 0) return;
+        unsigned units = 1 + (unsigned)((osize + 3) / 4);
+        unsigned long long at = 0;
+        if (lane == 0) at = atomicAdd(a.span_top16, (unsigned long long)units);
+        at = __shfl_sync(0xffffffffu, at, 0);
+        if (at + units > a.span_cap16) { err = 2; osize = 0; return; }       // span buffer full: the host grows it and redoes the pass
+        unsigned *sp = a.spans + 4 * (size_t)at;
+        if (lane == 0) {
+            sp[0] = (unsigned)osize; sp[1] = 0; sp[2] = 0; sp[3] = 0;
+            if (prev_span) a.spans[4 * (size_t)prev_span + 1] = (unsigned)at;
+        }
+        for (int k = lane; k < osize; k += 32) sp[4 + k] = obuf[k];
+        if (!first_span) first_span = (unsigned)at;
+        prev_span = (unsigned)at;
+        osize = 0;
+        __syncwarp();
+    };
+
+    while (true) {
+        // refill from the parent's list when the stack runs low
+        if (ssize < 32 && rd.more()) {
+            unsigned e = 0;
+            int n = rd.fetch(lane, e);
+            if (lane < n) stack[ssize + lane] = e;
+            ssize += n;
+            __syncwarp();
+            if (n > 0 && ssize < 32 && rd.more()) continue;
+        }
+        if (ssize == 0) break;
+        int k = ssize < 32 ? ssize : 32;
+        if (ssize > STACK_CAP - 64) k = 1;
+        const int sbase = ssize - k;
+        int npush = 0, emit_o = 0, emit_m = 0;
+        unsigned p0 = 0, p1 = 0, o0 = 0, o1 = 0, msrc = 0;
+        int no = 0;
+        if (lane < k) {
+            const unsigned jme = stack[sbase + lane];
+            const int jm = (int)(jme & PN2_CELL_MASK);
+            const unsigned img = jme >> PN2_IMG_SHIFT, imgbits = jme & ~PN2_CELL_MASK;
+            const bool lj = jm < a.nleaf;
+            if (img == 0 && jm == im) {
+                // walk(im, im): all four son combinations (src/fmm.c:429-436)
+                no = 2; o0 = (unsigned)a.son[2 * (size_t)im]; o1 = (unsigned)a.son[2 * (size_t)im + 1];
+            } else {
+                double cj[3], wj[3];
+                load_geom(a.geom, jm, cj, wj);
+                int pruned = 0;
+                if (img != 0) {
+                    if (!lj) pruned = pruned_dev(cj, wj, pc.shift[img], a.tc, a.tw, a.cutoff, a.theta, a.longshort);
+                    cj[0] += pc.shift[img][0]; cj[1] += pc.shift[img][1]; cj[2] += pc.shift[img][2];   // src/remotes.c:73-75
+                }
+                int f = accept_dev(wi, wj, ci[0] - cj[0], ci[1] - cj[1], ci[2] - cj[2], a.cutoff, a.theta, a.longshort);
+                if (f == 1) { emit_m = 1; msrc = jme; }
+                else if (f == 0) {
+                    // node x leaf: open the node; node x node: the one with the larger width sum, ties -> source
+                    // (src/fmm.c:518-527); a pruned remote node cannot be opened (src/remotes.c:351-357)
+                    bool open_i = lj || (swi > wj[0] + wj[1] + wj[2]) || (img != 0 && pruned);
+                    if (open_i) { no = 1; o0 = jme; }
+                    else {
+                        npush = 2;
+                        p0 = (unsigned)a.son[2 * (size_t)jm] | imgbits; p1 = (unsigned)a.son[2 * (size_t)jm + 1] | imgbits;
+                    }
+                }
+            }
+            emit_o = no;
+        }
+        visits += k;
+        __syncwarp();
+        const unsigned m2 = __ballot_sync(0xffffffffu, npush == 2);
+        int pos0 = sbase + 2 * __popc(m2 & lt_mask);
+        const int newsize = sbase + 2 * __popc(m2);
+        if (newsize > STACK_CAP) { err = 1; break; }
+        if (npush == 2) { stack[pos0] = p0; stack[pos0 + 1] = p1; }
+        ssize = newsize;
+        // O(im)
+        const unsigned mo1 = __ballot_sync(0xffffffffu, emit_o >= 1), mo2 = __ballot_sync(0xffffffffu, emit_o == 2);
+        const int nout = __popc(mo1) + __popc(mo2);
+        if (osize + nout > OBUF_CAP) flush();
+        if (emit_o >= 1) {
+            int at = osize + __popc(mo1 & lt_mask) + __popc(mo2 & lt_mask);
+            obuf[at] = o0;
+            if (emit_o == 2) obuf[at + 1] = o1;
+        }
+        osize += nout;
+        emit_m2l_pairs(a, lane, lt_mask, emit_m, (unsigned)im, msrc);
+        __syncwarp();
+        if (err) break;
+    }
+    flush();
+    if (lane == 0) {
+        a.o_head[im] = first_span;
+        if (err) atomicOr(&a.counters[3], (unsigned long long)err);
+        atomicAdd(&a.counters[4], visits);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pass 2: one warp per sink LEAF: F(leaf) = O(parent) -> source leaves -> P2P (and leaf-level M2L pairs)
+// ------------------------------------------------------------------------------------------------
 template <int SW, int MODE>     // MODE 0: FP32 P2P, 1: FP64 P2P, 2: dump lists (no arithmetic)
 __global__ void __launch_bounds__(WALK_WARPS * 32)
 walk_fused_kernel(WalkArgs a, P2PConst pc) {
     using ST = P2PStageF32<SW>;
     constexpr int NSL = 32 / SW;
-    __shared__ uint2 s_stack[WALK_WARPS][STACK_CAP];
+    __shared__ unsigned s_stack[WALK_WARPS][STACK_CAP];
     __shared__ unsigned s_srcq[WALK_WARPS][SRCQ_CAP];
-    __shared__ int s_anc[WALK_WARPS][MAX_DEPTH];
     __shared__ float4 s_stage[WALK_WARPS][2][ST::STAGE_F4];
 
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int leaf = blockIdx.x * WALK_WARPS + wib;
     if (leaf >= a.nleaf) return;
     const unsigned lt_mask = (1u << lane) - 1u;
-    uint2 *stack = s_stack[wib];
+    unsigned *stack = s_stack[wib];
     unsigned *srcq = s_srcq[wib];
-    int *anc = s_anc[wib];
 
-    // ---- ancestor chain and the depth from which this leaf is the designated M2L emitter ----
-    const int ldepth = a.depth[leaf];
-    int lm_depth = 0;
-    if (lane == 0) {
-        int c = leaf, d = ldepth, lm = ldepth;
-        bool left = true;
-        while (c >= 0) {
-            anc[d] = c;
-            int p = a.parent[c];
-            if (p >= 0 && left) {
-                if (a.son[2 * (size_t)p] == c) lm = d - 1; else left = false;
-            }
-            c = p; d--;
-        }
-        lm_depth = lm;
-    }
-    lm_depth = __shfl_sync(0xffffffffu, lm_depth, 0);
-    __syncwarp();
-
-    // ---- sink particles ----
+    // ---- sink leaf ----
     const int q = lane / SW, j = lane % SW;
     const LeafDesc sd = a.desc[leaf];
+    double ci[3], wi[3];
+    load_geom(a.geom, leaf, ci, wi);
     float xi = 0.f, yi = 0.f, zi = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
     double xd = 0, yd = 0, zd = 0, axd = 0, ayd = 0, azd = 0;
     if (MODE == 0 && j < sd.npart) { float4 p = a.rel[sd.first + j]; xi = p.x; yi = p.y; zi = p.z; }
@@ -136,11 +303,11 @@ walk_fused_kernel(WalkArgs a, P2PConst pc) {
 #pragma unroll
     for (int k = 0; k <= PN2_RDEG; k++) qc[k] = pc.q[k];
     const float inv_eps = pc.inv_eps;
-    unsigned long long nint = 0;
+    unsigned long long nint = 0, visits = 0;
     long npairs = 0;
     long dump_pos = (MODE == 2 && a.pass == 1) ? a.lst_off[leaf] : 0;
 
-    // ---- drain n entries of the source queue starting at qhead ----
+    // ---- drain entries of the source queue ----
     int qhead = 0, qtail = 0, buf = 0;
     auto load_stage = [&](int pos_, int limit) -> float4 {
         float4 p = make_float4(PN2_PAD_COORD, PN2_PAD_COORD, PN2_PAD_COORD, 0.f);
@@ -200,90 +367,60 @@ walk_fused_kernel(WalkArgs a, P2PConst pc) {
         __syncwarp();
     };
 
-    // ---- the walk ----
+    // ---- resolve F(leaf) ----
+    SpanReader rd;
+    rd.init(a.spans, a.o_head[a.parent[leaf]]);
     int ssize = 0;
-    if (lane < a.nimg) stack[lane] = make_uint2((unsigned)a.root, (unsigned)a.root | ((unsigned)lane << PN2_IMG_SHIFT));
-    ssize = a.nimg;
-    __syncwarp();
     int err = 0;
-
-    while (ssize > 0) {
+    while (true) {
+        if (ssize < 32 && rd.more()) {
+            unsigned e = 0;
+            int n = rd.fetch(lane, e);
+            if (lane < n) stack[ssize + lane] = e;
+            ssize += n;
+            __syncwarp();
+            if (n > 0 && ssize < 32 && rd.more()) continue;
+        }
+        if (ssize == 0) break;
         int k = ssize < 32 ? ssize : 32;
-        if (ssize > STACK_SOFT) k = 1;                       // depth-first when the stack is nearly full
+        if (ssize > STACK_CAP - 64) k = 1;
         const int sbase = ssize - k;
         int npush = 0, emit_p = 0, emit_m = 0;
-        unsigned p_im0 = 0, p_jm0 = 0, p_im1 = 0, p_jm1 = 0, m_src = 0, m_snk = 0, p_src = 0;
+        unsigned p0 = 0, p1 = 0, jme = 0;
         if (lane < k) {
-            uint2 ent = stack[sbase + lane];
-            const int im = (int)ent.x;
-            const unsigned jme = ent.y;
+            jme = stack[sbase + lane];
             const int jm = (int)(jme & PN2_CELL_MASK);
             const unsigned img = jme >> PN2_IMG_SHIFT, imgbits = jme & ~PN2_CELL_MASK;
-            const bool li = im < a.nleaf, lj = jm < a.nleaf;
-            if (img == 0 && im == jm) {
-                if (li) { emit_p = 1; p_src = jme; }
-                else {
-                    int t = anc[a.depth[im] + 1];
-                    npush = 2;
-                    p_im0 = p_im1 = (unsigned)t;
-                    p_jm0 = (unsigned)a.son[2 * (size_t)jm]; p_jm1 = (unsigned)a.son[2 * (size_t)jm + 1];
-                }
-            } else if (li && lj) {
-                emit_p = 1; p_src = jme;
+            if (jm < a.nleaf) {
+                emit_p = 1;            // leaf x leaf: always a P2P pair (src/fmm.c:438-451, src/remotes.c:228-240)
             } else {
-                const double *gi = a.geom + 6 * (size_t)im, *gj = a.geom + 6 * (size_t)jm;
-                double ci[3] = {gi[0], gi[1], gi[2]}, wi[3] = {gi[3], gi[4], gi[5]};
-                double cj[3] = {gj[0], gj[1], gj[2]}, wj[3] = {gj[3], gj[4], gj[5]};
+                double cj[3], wj[3];
+                load_geom(a.geom, jm, cj, wj);
                 int pruned = 0;
                 if (img != 0) {
-                    if (!lj) pruned = pruned_dev(cj, wj, pc.shift[img], a.tc, a.tw, a.cutoff, a.theta, a.longshort);
-                    cj[0] += pc.shift[img][0]; cj[1] += pc.shift[img][1]; cj[2] += pc.shift[img][2];   // src/remotes.c:73-75
+                    pruned = pruned_dev(cj, wj, pc.shift[img], a.tc, a.tw, a.cutoff, a.theta, a.longshort);
+                    cj[0] += pc.shift[img][0]; cj[1] += pc.shift[img][1]; cj[2] += pc.shift[img][2];
                 }
                 int f = accept_dev(wi, wj, ci[0] - cj[0], ci[1] - cj[1], ci[2] - cj[2], a.cutoff, a.theta, a.longshort);
-                if (f == -1) {
-                } else if (f == 1 || (img != 0 && li && pruned)) {
-                    // M2L jm -> im (a pruned remote node met by a local leaf is forced: src/remotes.c:442)
-                    if (a.depth[im] >= lm_depth) { emit_m = 1; m_src = jme; m_snk = (unsigned)im; }
-                } else {
-                    bool open_i;
-                    if (li) open_i = false;
-                    else if (lj) open_i = true;
-                    else open_i = (wi[0] + wi[1] + wi[2] > wj[0] + wj[1] + wj[2]) || (img != 0 && pruned);
-                    if (open_i) {
-                        npush = 1;
-                        p_im0 = (unsigned)anc[a.depth[im] + 1]; p_jm0 = jme;
-                    } else {
-                        npush = 2;
-                        p_im0 = p_im1 = (unsigned)im;
-                        p_jm0 = (unsigned)a.son[2 * (size_t)jm] | imgbits; p_jm1 = (unsigned)a.son[2 * (size_t)jm + 1] | imgbits;
-                    }
+                if (f == 1 || (f == 0 && pruned)) emit_m = 1;        // forced M2L on a pruned node: src/remotes.c:442
+                else if (f == 0) {
+                    npush = 2;
+                    p0 = (unsigned)a.son[2 * (size_t)jm] | imgbits; p1 = (unsigned)a.son[2 * (size_t)jm + 1] | imgbits;
                 }
             }
         }
+        visits += k;
         __syncwarp();
-        // pushes: second sons first so that the first son is popped first is not required (set semantics)
-        const unsigned m1 = __ballot_sync(0xffffffffu, npush >= 1), m2 = __ballot_sync(0xffffffffu, npush == 2);
-        int pos0 = sbase + __popc(m1 & lt_mask) + __popc(m2 & lt_mask);
-        const int newsize = sbase + __popc(m1) + __popc(m2);
+        const unsigned m2 = __ballot_sync(0xffffffffu, npush == 2);
+        int pos0 = sbase + 2 * __popc(m2 & lt_mask);
+        const int newsize = sbase + 2 * __popc(m2);
         if (newsize > STACK_CAP) { err = 1; break; }
-        if (npush >= 1) stack[pos0] = make_uint2(p_im0, p_jm0);
-        if (npush == 2) stack[pos0 + 1] = make_uint2(p_im1, p_jm1);
+        if (npush == 2) { stack[pos0] = p0; stack[pos0 + 1] = p1; }
         ssize = newsize;
-        // P2P sources -> queue
         const unsigned mp = __ballot_sync(0xffffffffu, emit_p);
-        if (emit_p) srcq[(qtail + __popc(mp & lt_mask)) & (SRCQ_CAP - 1)] = p_src;
+        if (emit_p) srcq[(qtail + __popc(mp & lt_mask)) & (SRCQ_CAP - 1)] = jme;
         qtail += __popc(mp);
-        // M2L pairs -> global list
-        const unsigned mm = __ballot_sync(0xffffffffu, emit_m);
-        if (mm && a.emit_m2l) {
-            unsigned long long basei = 0;
-            if (lane == 0) basei = atomicAdd(&a.counters[1], (unsigned long long)__popc(mm));
-            basei = __shfl_sync(0xffffffffu, basei, 0);
-            if (emit_m) {
-                unsigned long long at = basei + __popc(mm & lt_mask);
-                if (at < a.m2l_cap) { a.m2l_t[at] = m_snk; a.m2l_s[at] = m_src; }
-            }
-        }
+        emit_m2l_pairs(a, lane, lt_mask, emit_m, (unsigned)leaf, jme);
         __syncwarp();
         if (qtail - qhead >= 32) drain(qhead + ((qtail - qhead) / NSL) * NSL);
     }
@@ -323,6 +460,7 @@ walk_fused_kernel(WalkArgs a, P2PConst pc) {
         if (lane == 0) {
             atomicAdd(&a.counters[0], nint * (unsigned long long)sd.npart);
             atomicAdd(&a.counters[2], (unsigned long long)npairs);
+            atomicAdd(&a.counters[4], visits);
         }
     }
 }
@@ -336,15 +474,10 @@ static void launch_mode(pn2_ctx *h, const WalkArgs &a, int mode) {
     h->launches++;
 }
 
-// dump = 0: the product step (P2P evaluated, M2L pairs appended to h->m2l_pairs);
-// dump = 1 / 2: list dump passes (count / fill) for pn2_get_lists
-int pn2_walk_fused(pn2_ctx *h, int dump) {
-    if (h->nleaf == 0) return PN2_OK;
-    if (h->nlevel + 1 >= MAX_DEPTH) { pn2_set_error("pn2: tree depth %d exceeds %d", h->nlevel, MAX_DEPTH - 2); return PN2_ERR_ARG; }
-    WalkArgs a;
+static void fill_args(pn2_ctx *h, WalkArgs &a) {
     memset(&a, 0, sizeof a);
     a.nleaf = h->nleaf; a.ncell = h->ncell; a.root = h->nleaf;
-    a.geom = h->geom.p; a.son = h->son.p; a.desc = h->desc.p; a.parent = h->parent.p; a.depth = h->depth.p;
+    a.geom = h->geom.p; a.son = h->son.p; a.desc = h->desc.p; a.parent = h->parent.p;
     a.rel = h->rel.p; a.pos = h->pos.p; a.acc = h->acc.p;
     a.cutoff = h->prm.cutoff; a.theta = h->prm.theta; a.longshort = h->prm.longshort; a.maxleaf = h->prm.maxleaf;
     a.nimg = h->prm.periodic ? 27 : 1;
@@ -353,9 +486,36 @@ int pn2_walk_fused(pn2_ctx *h, int dump) {
         a.tc[d] = 0.5 * (h->dom.hi[d] + h->dom.lo[d]);
         a.tw[d] = h->dom.hi[d] - h->dom.lo[d];
     }
+    a.spans = h->spans.p; a.span_cap16 = h->span_cap16; a.span_top16 = h->counters.p + 6; a.o_head = h->o_head.p;
     a.m2l_t = h->m2l_pairs.p; a.m2l_s = h->m2l_pairs.p + h->m2l_cap; a.m2l_cap = h->m2l_cap;
     a.counters = h->counters.p;
     a.lst_off = h->lst_off.p; a.lst_src = h->lst_src.p;
+}
+
+// Pass 1 over all levels.  counters[6] is the span bump pointer (unit 0 is reserved: 0 = "no span").
+int pn2_walk_frontiers(pn2_ctx *h) {
+    if (h->nnode == 0) return PN2_OK;
+    WalkArgs a;
+    fill_args(h, a);
+    a.emit_m2l = 1;
+    for (int lev = 0; lev < h->nlevel; lev++) {
+        int cnt = h->level_off[lev + 1] - h->level_off[lev];
+        if (cnt == 0) continue;
+        a.work = h->level_nodes.p + h->level_off[lev];
+        a.nwork = cnt;
+        frontier_node_kernel<<<(cnt + WALK_WARPS - 1) / WALK_WARPS, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
+        h->launches++;
+    }
+    KERNEL_CHECK();
+    return PN2_OK;
+}
+
+// dump = 0: the product step (P2P evaluated, leaf-level M2L pairs appended);
+// dump = 1 / 2: list dump passes (count / fill) for pn2_get_lists
+int pn2_walk_fused(pn2_ctx *h, int dump) {
+    if (h->nleaf == 0) return PN2_OK;
+    WalkArgs a;
+    fill_args(h, a);
     a.pass = dump == 2 ? 1 : 0;
     a.emit_m2l = dump == 0;
     int mode = dump ? 2 : (h->prm.precision == PN2_FP64 ? 1 : 0);

@@ -51,7 +51,8 @@ class Domain(C.Structure):
 class StepInfo(C.Structure):
     _fields_ = [("n", C.c_int32), ("nleaf", C.c_int32), ("nnode", C.c_int32), ("nlevel", C.c_int32),
                 ("n_p2p_pairs", C.c_int64), ("n_m2l_pairs", C.c_int64), ("n_interactions", C.c_int64),
-                ("n_let_nodes", C.c_int64), ("n_let_bodies", C.c_int64)]
+                ("n_let_nodes", C.c_int64), ("n_let_bodies", C.c_int64), ("n_walk_visits", C.c_int64),
+                ("frontier_bytes", C.c_int64)]
 
 
 def make_params(box, nside, npart_total, mass, maxleaf=8, theta=0.4, split=-1.0, soft=-1.0, periodic=1, longshort=1,
@@ -299,7 +300,7 @@ class Context:
     def timings(self):
         t = np.zeros(8)
         _ck(lib().pn2_get_timings(self.h, t.ctypes.data_as(C.POINTER(C.c_double))))
-        return dict(zip(["tree", "upward", "walk_p2p", "m2l", "downward", "let", "total", "_"], t))
+        return dict(zip(["tree", "upward", "walk_p2p", "m2l", "downward", "let", "total", "frontier"], t))
 
     def fma_peak(self, fp64=False):
         ops, ms = C.c_double(), C.c_double()
