@@ -26,6 +26,9 @@
 #define STACK_CAP 512
 #define SRCQ_CAP 64
 #define OBUF_CAP 256              // per-warp staging of O(im) before it is flushed to a span
+#ifndef LEAF_MIN_BLOCKS
+#define LEAF_MIN_BLOCKS 7          // register cap of the leaf kernel (72 regs, 28 warps/SM): best of 5..8 measured at 256^3
+#endif
 
 struct WalkArgs {
     int nleaf, ncell, root;
@@ -274,27 +277,37 @@ __global__ void __launch_bounds__(WALK_WARPS * 32) frontier_node_kernel(WalkArgs
 // ------------------------------------------------------------------------------------------------
 // Pass 2: one warp per sink LEAF: F(leaf) = O(parent) -> source leaves -> P2P (and leaf-level M2L pairs)
 // ------------------------------------------------------------------------------------------------
+// A resolved source leaf in the per-warp queue: everything the stage loader needs, computed once by the
+// lane that found it (not by the 8 lanes that later load its particles)
+struct __align__(16) SrcEnt {
+    int first, npart;       // particle range
+    unsigned tag;           // cell | image << 26 (dump mode, FP64 mode)
+    float dx, dy, dz;       // source leaf centre - sink leaf centre (+ image shift), units of 2 rs
+    float pad0, pad1;
+};
+
 template <int SW, int MODE>     // MODE 0: FP32 P2P, 1: FP64 P2P, 2: dump lists (no arithmetic)
-__global__ void __launch_bounds__(WALK_WARPS * 32)
+__global__ void __launch_bounds__(WALK_WARPS * 32, LEAF_MIN_BLOCKS)
 walk_fused_kernel(WalkArgs a, P2PConst pc) {
     using ST = P2PStageF32<SW>;
     constexpr int NSL = 32 / SW;
     __shared__ unsigned s_stack[WALK_WARPS][STACK_CAP];
-    __shared__ unsigned s_srcq[WALK_WARPS][SRCQ_CAP];
+    __shared__ SrcEnt s_srcq[WALK_WARPS][SRCQ_CAP];
     __shared__ float4 s_stage[WALK_WARPS][2][ST::STAGE_F4];
+    __shared__ double s_sink[WALK_WARPS][6];
 
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int leaf = blockIdx.x * WALK_WARPS + wib;
     if (leaf >= a.nleaf) return;
     const unsigned lt_mask = (1u << lane) - 1u;
     unsigned *stack = s_stack[wib];
-    unsigned *srcq = s_srcq[wib];
+    SrcEnt *srcq = s_srcq[wib];
+    const double *sink_g = s_sink[wib];
 
     // ---- sink leaf ----
     const int q = lane / SW, j = lane % SW;
     const LeafDesc sd = a.desc[leaf];
-    double ci[3], wi[3];
-    load_geom(a.geom, leaf, ci, wi);
+    if (lane < 6) s_sink[wib][lane] = a.geom[6 * (size_t)leaf + lane];
     float xi = 0.f, yi = 0.f, zi = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
     double xd = 0, yd = 0, zd = 0, axd = 0, ayd = 0, azd = 0;
     if (MODE == 0 && j < sd.npart) { float4 p = a.rel[sd.first + j]; xi = p.x; yi = p.y; zi = p.z; }
@@ -303,27 +316,23 @@ walk_fused_kernel(WalkArgs a, P2PConst pc) {
 #pragma unroll
     for (int k = 0; k <= PN2_RDEG; k++) qc[k] = pc.q[k];
     const float inv_eps = pc.inv_eps;
-    unsigned long long nint = 0, visits = 0;
-    long npairs = 0;
+    unsigned nsrc = 0, visits = 0, npairs = 0;
     long dump_pos = (MODE == 2 && a.pass == 1) ? a.lst_off[leaf] : 0;
+    __syncwarp();
 
-    // ---- drain entries of the source queue ----
+    // ---- drain entries of the source queue through the staged P2P pipeline ----
     int qhead = 0, qtail = 0, buf = 0;
     auto load_stage = [&](int pos_, int limit) -> float4 {
         float4 p = make_float4(PN2_PAD_COORD, PN2_PAD_COORD, PN2_PAD_COORD, 0.f);
         int idx = pos_ + q;
         if (idx < limit) {
-            unsigned e = srcq[idx & (SRCQ_CAP - 1)];
-            unsigned cell = e & PN2_CELL_MASK, img = e >> PN2_IMG_SHIFT;
-            LeafDesc d = a.desc[cell];
-            if (j < d.npart) {
-                float4 r = a.rel[d.first + j];
-                float Dx = (float)(((d.c[0] + pc.shift[img][0]) - sd.c[0]) * pc.inv2rs);
-                float Dy = (float)(((d.c[1] + pc.shift[img][1]) - sd.c[1]) * pc.inv2rs);
-                float Dz = (float)(((d.c[2] + pc.shift[img][2]) - sd.c[2]) * pc.inv2rs);
-                p = make_float4(r.x + Dx, r.y + Dy, r.z + Dz, 1.f);
+            const SrcEnt *e = &srcq[idx & (SRCQ_CAP - 1)];
+            const int4 h4 = *reinterpret_cast<const int4 *>(e);           // first, npart, tag, dx
+            if (j < h4.y) {
+                const float2 d2 = *reinterpret_cast<const float2 *>(&e->dy);
+                float4 r = a.rel[h4.x + j];
+                p = make_float4(r.x + __int_as_float(h4.w), r.y + d2.x, r.z + d2.y, 1.f);
             }
-            if (j == 0) nint += (unsigned long long)(d.npart - ((e == (unsigned)leaf) ? 1 : 0));
         }
         return p;
     };
@@ -346,20 +355,18 @@ walk_fused_kernel(WalkArgs a, P2PConst pc) {
             }
         } else if (MODE == 1) {
             for (int idx = qhead + q; idx < limit; idx += NSL) {
-                unsigned e = srcq[idx & (SRCQ_CAP - 1)];
-                unsigned cell = e & PN2_CELL_MASK, img = e >> PN2_IMG_SHIFT;
-                LeafDesc d = a.desc[cell];
+                const SrcEnt e = srcq[idx & (SRCQ_CAP - 1)];
+                const unsigned img = e.tag >> PN2_IMG_SHIFT;
                 const double sx = pc.shift[img][0], sy = pc.shift[img][1], sz = pc.shift[img][2];
-                for (int k = 0; k < d.npart; k++) {
-                    const double *p = a.pos + 3 * (size_t)(d.first + k);
+                for (int k = 0; k < e.npart; k++) {
+                    const double *p = a.pos + 3 * (size_t)(e.first + k);
                     p2p_interact_f64(p[0] + sx, p[1] + sy, p[2] + sz, pc.mass, xd, yd, zd, axd, ayd, azd, pc.soft,
                                      pc.inv2rs, pc.longshort);
                 }
-                if (j == 0) nint += (unsigned long long)(d.npart - ((e == (unsigned)leaf) ? 1 : 0));
             }
         } else {
             if (a.pass == 1)
-                for (int idx = qhead + lane; idx < limit; idx += 32) a.lst_src[dump_pos + (idx - qhead)] = srcq[idx & (SRCQ_CAP - 1)];
+                for (int idx = qhead + lane; idx < limit; idx += 32) a.lst_src[dump_pos + (idx - qhead)] = srcq[idx & (SRCQ_CAP - 1)].tag;
             dump_pos += limit - qhead;
         }
         npairs += limit - qhead;
@@ -387,12 +394,21 @@ walk_fused_kernel(WalkArgs a, P2PConst pc) {
         const int sbase = ssize - k;
         int npush = 0, emit_p = 0, emit_m = 0;
         unsigned p0 = 0, p1 = 0, jme = 0;
+        SrcEnt ent;
         if (lane < k) {
             jme = stack[sbase + lane];
             const int jm = (int)(jme & PN2_CELL_MASK);
             const unsigned img = jme >> PN2_IMG_SHIFT, imgbits = jme & ~PN2_CELL_MASK;
             if (jm < a.nleaf) {
-                emit_p = 1;            // leaf x leaf: always a P2P pair (src/fmm.c:438-451, src/remotes.c:228-240)
+                // leaf x leaf: always a P2P pair (src/fmm.c:438-451, src/remotes.c:228-240)
+                emit_p = 1;
+                const LeafDesc d = a.desc[jm];
+                ent.first = d.first; ent.npart = d.npart; ent.tag = jme;
+                ent.dx = (float)(((d.c[0] + pc.shift[img][0]) - sd.c[0]) * pc.inv2rs);
+                ent.dy = (float)(((d.c[1] + pc.shift[img][1]) - sd.c[1]) * pc.inv2rs);
+                ent.dz = (float)(((d.c[2] + pc.shift[img][2]) - sd.c[2]) * pc.inv2rs);
+                ent.pad0 = 0.f; ent.pad1 = 0.f;
+                nsrc += (unsigned)(d.npart - ((jme == (unsigned)leaf) ? 1 : 0));
             } else {
                 double cj[3], wj[3];
                 load_geom(a.geom, jm, cj, wj);
@@ -401,7 +417,8 @@ walk_fused_kernel(WalkArgs a, P2PConst pc) {
                     pruned = pruned_dev(cj, wj, pc.shift[img], a.tc, a.tw, a.cutoff, a.theta, a.longshort);
                     cj[0] += pc.shift[img][0]; cj[1] += pc.shift[img][1]; cj[2] += pc.shift[img][2];
                 }
-                int f = accept_dev(wi, wj, ci[0] - cj[0], ci[1] - cj[1], ci[2] - cj[2], a.cutoff, a.theta, a.longshort);
+                int f = accept_dev(sink_g + 3, wj, sink_g[0] - cj[0], sink_g[1] - cj[1], sink_g[2] - cj[2], a.cutoff, a.theta,
+                                   a.longshort);
                 if (f == 1 || (f == 0 && pruned)) emit_m = 1;        // forced M2L on a pruned node: src/remotes.c:442
                 else if (f == 0) {
                     npush = 2;
@@ -418,7 +435,11 @@ walk_fused_kernel(WalkArgs a, P2PConst pc) {
         if (npush == 2) { stack[pos0] = p0; stack[pos0 + 1] = p1; }
         ssize = newsize;
         const unsigned mp = __ballot_sync(0xffffffffu, emit_p);
-        if (emit_p) srcq[(qtail + __popc(mp & lt_mask)) & (SRCQ_CAP - 1)] = jme;
+        if (emit_p) {
+            SrcEnt *dst = &srcq[(qtail + __popc(mp & lt_mask)) & (SRCQ_CAP - 1)];
+            *reinterpret_cast<int4 *>(dst) = make_int4(ent.first, ent.npart, (int)ent.tag, __float_as_int(ent.dx));
+            *reinterpret_cast<float4 *>(&dst->dy) = make_float4(ent.dy, ent.dz, 0.f, 0.f);
+        }
         qtail += __popc(mp);
         emit_m2l_pairs(a, lane, lt_mask, emit_m, (unsigned)leaf, jme);
         __syncwarp();
@@ -452,15 +473,15 @@ walk_fused_kernel(WalkArgs a, P2PConst pc) {
             o[0] += axd; o[1] += ayd; o[2] += azd;
         }
     } else {
-        if (a.pass == 0 && lane == 0) a.lst_off[leaf] = npairs;
+        if (a.pass == 0 && lane == 0) a.lst_off[leaf] = (long)npairs;
     }
     if (MODE != 2) {
 #pragma unroll
-        for (int m = SW; m < 32; m <<= 1) nint += __shfl_xor_sync(0xffffffffu, nint, m);
+        for (int m = 1; m < 32; m <<= 1) nsrc += __shfl_xor_sync(0xffffffffu, nsrc, m);
         if (lane == 0) {
-            atomicAdd(&a.counters[0], nint * (unsigned long long)sd.npart);
+            atomicAdd(&a.counters[0], (unsigned long long)nsrc * (unsigned long long)sd.npart);
             atomicAdd(&a.counters[2], (unsigned long long)npairs);
-            atomicAdd(&a.counters[4], visits);
+            atomicAdd(&a.counters[4], (unsigned long long)visits);
         }
     }
 }
