@@ -153,6 +153,19 @@ int pn2_force_step_device(pn2_ctx *h, const double *d_pos, int n, const pn2_doma
  * exchanged with grouped ncclSend/ncclRecv (replaces src/remotes.c:684-751). */
 int pn2_set_comm(pn2_ctx *h, int rank, int nranks, const pn2_domain *all_domains, void *nccl_comm);
 
+/* Own communicator: rank 0 calls pn2_comm_unique_id and broadcasts the 128 bytes (any host transport); every rank then
+ * calls pn2_comm_init_rank (ncclCommInitRank).  The context destroys the communicator it created. */
+int pn2_comm_unique_id(void *out128);
+int pn2_comm_init_rank(pn2_ctx *h, int rank, int nranks, const pn2_domain *all_domains, const void *id128);
+
+/* The two halves of pn2_force_step_device, for drivers that own the exchange: begin = tree + upward pass + LET
+ * pack for every peer; finish = LET unpack + lists + P2P + M2L + downward pass.  Between them the LET blocks must be
+ * exchanged: pn2_force_step_device does it with NCCL; pn2_exchange_local does it with device-to-device copies
+ * when all ranks are contexts of ONE process (hs[r] = the context of rank r). */
+int pn2_step_begin(pn2_ctx *h, const double *d_pos, int n, const pn2_domain *dom);
+int pn2_exchange_local(pn2_ctx **hs, int nranks);
+int pn2_step_finish(pn2_ctx *h, double *d_acc);
+
 /* ---- Mode B inspection (tests: bit-exact tree / list checks; not needed by the product path) --- */
 typedef struct {
     int32_t n, nleaf, nnode, nlevel;

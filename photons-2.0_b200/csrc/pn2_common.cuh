@@ -145,11 +145,17 @@ struct pn2_ctx {
     pn2_domain dom{};
     pn2_step_info info{};
     bool have_step = false;
-    // multi-rank
+    // multi-rank: received LET cells are appended to the cell arrays (leaves then nodes), ghost particles to rel / pos
+    int nrl = 0, nrn = 0, nrp = 0;
+    unsigned root_head = 0;
     int rank = 0, nranks = 1;
+    bool own_comm = false;
+    struct LetState *let = nullptr;
     std::vector<pn2_domain> all_dom;
     void *nccl = nullptr;
-    cudaEvent_t ev[8] = {nullptr};
+    cudaEvent_t ev[10] = {nullptr};
+    bool step_open = false;
+    unsigned root_units = 0;
     cudaEvent_t tev[4][2] = {{nullptr}};
 };
 
@@ -166,4 +172,11 @@ int pn2_csr_from_device_pairs(pn2_ctx *h, int *tcell, unsigned *scell, long n, C
 int pn2_tree_build_device(pn2_ctx *h, const double *d_pos_in, int n, const pn2_domain *dom);
 int pn2_walk_fused(pn2_ctx *h, int dump);
 int pn2_walk_frontiers(pn2_ctx *h);
+int pn2_let_pack_all(pn2_ctx *h);
+int pn2_let_exchange_nccl(pn2_ctx *h);
+int pn2_let_unpack(pn2_ctx *h);
+void pn2_let_release(pn2_ctx *h);
+void pn2_comm_release(pn2_ctx *h);
+int pn2_step_begin(pn2_ctx *h, const double *d_pos, int n, const pn2_domain *dom);
+int pn2_step_finish(pn2_ctx *h, double *d_acc);
 void pn2_init_consts(pn2_ctx *h);

@@ -11,7 +11,9 @@ void pn2_modeb_release(pn2_ctx *h) {
     h->n_start.release(); h->n_count.release(); h->n_son.release(); h->n_depth.release(); h->l_start.release();
     h->l_count.release(); h->n_box.release(); h->n_split.release(); h->l_box.release(); h->b_cnt.release();
     h->b_scal.release(); h->m2l_pairs.release(); h->spans.release(); h->o_head.release(); h->lst_off.release(); h->lst_src.release(); h->lst_sink.release();
-    for (int i = 0; i < 8; i++) if (h->ev[i]) { cudaEventDestroy(h->ev[i]); h->ev[i] = nullptr; }
+    for (int i = 0; i < 10; i++) if (h->ev[i]) { cudaEventDestroy(h->ev[i]); h->ev[i] = nullptr; }
+    pn2_let_release(h);
+    pn2_comm_release(h);
 }
 
 __global__ void scatter_acc_kernel(int n, const double *__restrict__ acc, const int *__restrict__ order,
@@ -29,32 +31,51 @@ __global__ void iota_kernel(int n, int *o) {
 }
 
 static int ensure_events(pn2_ctx *h) {
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < 10; i++)
         if (!h->ev[i]) CUDA_TRY(cudaEventCreate(&h->ev[i]));
     return PN2_OK;
 }
 
-extern "C" int pn2_force_step_device(pn2_ctx *h, const double *d_pos, int n, const pn2_domain *dom, double *d_acc) {
-    if (!h || n < 0 || !dom || (n > 0 && (!d_pos || !d_acc))) { pn2_set_error("pn2_force_step_device: bad argument"); return PN2_ERR_ARG; }
+// Phase 1 of a step: tree, upward pass and (multi-rank) the LET packs for every peer
+extern "C" int pn2_step_begin(pn2_ctx *h, const double *d_pos, int n, const pn2_domain *dom) {
+    if (!h || n < 0 || !dom || (n > 0 && !d_pos)) { pn2_set_error("pn2_step_begin: bad argument"); return PN2_ERR_ARG; }
     for (int d = 0; d < 3; d++)
-        if (!(dom->hi[d] > dom->lo[d])) { pn2_set_error("pn2_force_step_device: empty domain box"); return PN2_ERR_ARG; }
-    if (dom->direct0 < 0 || dom->direct0 > 2) { pn2_set_error("pn2_force_step_device: direct0 must be 0..2"); return PN2_ERR_ARG; }
+        if (!(dom->hi[d] > dom->lo[d])) { pn2_set_error("pn2_step_begin: empty domain box"); return PN2_ERR_ARG; }
+    if (dom->direct0 < 0 || dom->direct0 > 2) { pn2_set_error("pn2_step_begin: direct0 must be 0..2"); return PN2_ERR_ARG; }
     CUDA_TRY(cudaSetDevice(h->device));
     PN2_TRY(ensure_events(h));
     cudaStream_t st = h->stream;
     h->have_step = false;
+    h->step_open = false;
     memset(&h->info, 0, sizeof h->info);
     CUDA_TRY(cudaEventRecord(h->ev[0], st));
     PN2_TRY(pn2_tree_build_device(h, d_pos, n, dom));
     CUDA_TRY(cudaEventRecord(h->ev[1], st));
     h->info.n = n; h->info.nleaf = h->nleaf; h->info.nnode = h->nnode; h->info.nlevel = h->nlevel;
-    if (n == 0) { h->have_step = true; return PN2_OK; }
-    // upward pass
-    if (h->prm.precision == PN2_FP32) PN2_TRY(pn2_launch_relpos(h, h->pos.p, h->desc.p, h->nleaf, h->rel.p, n));
-    PN2_TRY(pn2_launch_p2m(h));
-    PN2_TRY(pn2_launch_m2m(h));
+    if (n > 0) {
+        if (h->prm.precision == PN2_FP32) PN2_TRY(pn2_launch_relpos(h, h->pos.p, h->desc.p, h->nleaf, h->rel.p, n));
+        PN2_TRY(pn2_launch_p2m(h));
+        PN2_TRY(pn2_launch_m2m(h));
+    }
     CUDA_TRY(cudaEventRecord(h->ev[2], st));
-    // fused walk + P2P (local pairs and the 26 periodic images)
+    if (h->nranks > 1) PN2_TRY(pn2_let_pack_all(h));
+    CUDA_TRY(cudaEventRecord(h->ev[7], st));
+    h->step_open = true;
+    return PN2_OK;
+}
+
+// Phase 2 (after the LET exchange): lists + P2P, M2L, downward pass, accelerations in caller order
+extern "C" int pn2_step_finish(pn2_ctx *h, double *d_acc) {
+    if (!h || !h->step_open || (h->n > 0 && !d_acc)) { pn2_set_error("pn2_step_finish: no open step / bad argument"); return PN2_ERR_ARG; }
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const int n = h->n;
+    h->step_open = false;
+    if (n == 0) {
+        for (int i = 3; i < 7; i++) CUDA_TRY(cudaEventRecord(h->ev[i], st));
+        h->have_step = true;
+        return PN2_OK;
+    }
     if (h->m2l_cap == 0) {
         size_t cap = 4u << 20;
         PN2_TRY(h->m2l_pairs.ensure(2 * cap));
@@ -67,10 +88,12 @@ extern "C" int pn2_force_step_device(pn2_ctx *h, const double *d_pos, int n, con
         h->spans.release();
         PN2_TRY(h->spans.ensure(4 * (size_t)h->span_cap16));
     }
+    PN2_TRY(pn2_let_unpack(h));                                        // also writes F(root) into the span buffer
+    CUDA_TRY(cudaEventRecord(h->ev[8], st));
     for (int attempt = 0;; attempt++) {
         CUDA_TRY(cudaMemsetAsync(h->counters.p, 0, 8 * sizeof(unsigned long long), st));
-        const unsigned long long one = 1;                              // span unit 0 is reserved (0 = empty list)
-        CUDA_TRY(cudaMemcpyAsync(h->counters.p + 6, &one, sizeof one, cudaMemcpyHostToDevice, st));
+        const unsigned long long top0 = 1 + (unsigned long long)h->root_units;   // unit 0 reserved (0 = empty list), then F(root)
+        CUDA_TRY(cudaMemcpyAsync(h->counters.p + 6, &top0, sizeof top0, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemsetAsync(h->o_head.p, 0, ((size_t)h->ncell + 1) * sizeof(unsigned), st));
         PN2_TRY(pn2_walk_frontiers(h));
         if (attempt == 0) CUDA_TRY(cudaEventRecord(h->ev[6], st));
@@ -85,6 +108,7 @@ extern "C" int pn2_force_step_device(pn2_ctx *h, const double *d_pos, int n, con
             h->span_cap16 = want;
             h->spans.release();
             PN2_TRY(h->spans.ensure(4 * (size_t)h->span_cap16));
+            PN2_TRY(pn2_let_unpack(h));                                // rewrite F(root) into the new buffer
             redo = true;
         }
         if (cnt[1] > h->m2l_cap) {                                     // M2L pair buffer too small
@@ -119,6 +143,13 @@ extern "C" int pn2_force_step_device(pn2_ctx *h, const double *d_pos, int n, con
     return PN2_OK;
 }
 
+extern "C" int pn2_force_step_device(pn2_ctx *h, const double *d_pos, int n, const pn2_domain *dom, double *d_acc) {
+    if (h && n > 0 && !d_acc) { pn2_set_error("pn2_force_step_device: bad argument"); return PN2_ERR_ARG; }
+    PN2_TRY(pn2_step_begin(h, d_pos, n, dom));
+    if (h->nranks > 1) PN2_TRY(pn2_let_exchange_nccl(h));
+    return pn2_step_finish(h, d_acc);
+}
+
 extern "C" int pn2_force_step(pn2_ctx *h, const double *pos, size_t pos_stride, int n, const pn2_domain *dom, double *acc,
                               size_t acc_stride) {
     if (!h || n < 0 || (n > 0 && (!pos || !acc)) || pos_stride < 24 || acc_stride < 24 || pos_stride % 8 || acc_stride % 8) {
@@ -145,7 +176,7 @@ extern "C" int pn2_set_comm(pn2_ctx *h, int rank, int nranks, const pn2_domain *
     if (!h || nranks < 1 || rank < 0 || rank >= nranks || !all) { pn2_set_error("pn2_set_comm: bad argument"); return PN2_ERR_ARG; }
     h->rank = rank; h->nranks = nranks; h->nccl = comm;
     h->all_dom.assign(all, all + nranks);
-    if (nranks > 1) { pn2_set_error("pn2_set_comm: multi-rank LET exchange is not built yet"); return PN2_ERR_STATE; }
+    h->own_comm = false;
     return PN2_OK;
 }
 
@@ -245,7 +276,8 @@ extern "C" int pn2_get_timings(pn2_ctx *h, double ms[8]) {
     float t = 0;
     CUDA_TRY(cudaEventElapsedTime(&t, h->ev[0], h->ev[1])); ms[0] = t;     // tree
     CUDA_TRY(cudaEventElapsedTime(&t, h->ev[1], h->ev[2])); ms[1] = t;     // upward
-    CUDA_TRY(cudaEventElapsedTime(&t, h->ev[2], h->ev[6])); ms[7] = t;     // frontier pass (lists by sink node)
+    CUDA_TRY(cudaEventElapsedTime(&t, h->ev[2], h->ev[8])); ms[5] = t;     // LET pack + exchange + unpack
+    CUDA_TRY(cudaEventElapsedTime(&t, h->ev[8], h->ev[6])); ms[7] = t;     // frontier pass (lists by sink node)
     CUDA_TRY(cudaEventElapsedTime(&t, h->ev[6], h->ev[3])); ms[2] = t;     // fused leaf walk + P2P
     CUDA_TRY(cudaEventElapsedTime(&t, h->ev[3], h->ev[4])); ms[3] = t;     // M2L
     CUDA_TRY(cudaEventElapsedTime(&t, h->ev[4], h->ev[5])); ms[4] = t;     // downward

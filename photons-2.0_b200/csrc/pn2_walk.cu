@@ -31,7 +31,9 @@
 #endif
 
 struct WalkArgs {
-    int nleaf, ncell, root;
+    int nleaf, ncell, root;            // LOCAL leaves / cells; root = local root cell
+    int rleaf0, rnode0;                // received LET cells: leaves [rleaf0, rnode0), nodes [rnode0, ...)
+    unsigned root_head;                // span holding F(root): (root | image) of the local tree and of every peer's tree
     const double *geom;
     const int *son;
     const LeafDesc *desc;
@@ -164,14 +166,8 @@ __global__ void __launch_bounds__(WALK_WARPS * 32) frontier_node_kernel(WalkArgs
     const double swi = wi[0] + wi[1] + wi[2];
 
     SpanReader rd;
-    if (im == a.root) {
-        rd.init(a.spans, 0);
-        if (lane < a.nimg) stack[lane] = (unsigned)a.root | ((unsigned)lane << PN2_IMG_SHIFT);
-    } else {
-        rd.init(a.spans, a.o_head[a.parent[im]]);
-    }
-    int ssize = (im == a.root) ? a.nimg : 0;
-    __syncwarp();
+    rd.init(a.spans, im == a.root ? a.root_head : a.o_head[a.parent[im]]);
+    int ssize = 0;
 
     int osize = 0;
     unsigned first_span = 0, prev_span = 0;
@@ -217,7 +213,8 @@ __global__ void __launch_bounds__(WALK_WARPS * 32) frontier_node_kernel(WalkArgs
             const unsigned jme = stack[sbase + lane];
             const int jm = (int)(jme & PN2_CELL_MASK);
             const unsigned img = jme >> PN2_IMG_SHIFT, imgbits = jme & ~PN2_CELL_MASK;
-            const bool lj = jm < a.nleaf;
+            const bool lj = jm < a.nleaf || (jm >= a.rleaf0 && jm < a.rnode0);
+            const bool remote = img != 0 || jm >= a.rleaf0;          // walk_task_*_ext rules (src/remotes.c)
             if (img == 0 && jm == im) {
                 // walk(im, im): all four son combinations (src/fmm.c:429-436)
                 no = 2; o0 = (unsigned)a.son[2 * (size_t)im]; o1 = (unsigned)a.son[2 * (size_t)im + 1];
@@ -225,7 +222,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32) frontier_node_kernel(WalkArgs
                 double cj[3], wj[3];
                 load_geom(a.geom, jm, cj, wj);
                 int pruned = 0;
-                if (img != 0) {
+                if (remote) {
                     if (!lj) pruned = pruned_dev(cj, wj, pc.shift[img], a.tc, a.tw, a.cutoff, a.theta, a.longshort);
                     cj[0] += pc.shift[img][0]; cj[1] += pc.shift[img][1]; cj[2] += pc.shift[img][2];   // src/remotes.c:73-75
                 }
@@ -234,7 +231,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32) frontier_node_kernel(WalkArgs
                 else if (f == 0) {
                     // node x leaf: open the node; node x node: the one with the larger width sum, ties -> source
                     // (src/fmm.c:518-527); a pruned remote node cannot be opened (src/remotes.c:351-357)
-                    bool open_i = lj || (swi > wj[0] + wj[1] + wj[2]) || (img != 0 && pruned);
+                    bool open_i = lj || (swi > wj[0] + wj[1] + wj[2]) || pruned;
                     if (open_i) { no = 1; o0 = jme; }
                     else {
                         npush = 2;
@@ -399,7 +396,7 @@ walk_fused_kernel(WalkArgs a, P2PConst pc) {
             jme = stack[sbase + lane];
             const int jm = (int)(jme & PN2_CELL_MASK);
             const unsigned img = jme >> PN2_IMG_SHIFT, imgbits = jme & ~PN2_CELL_MASK;
-            if (jm < a.nleaf) {
+            if (jm < a.nleaf || (jm >= a.rleaf0 && jm < a.rnode0)) {
                 // leaf x leaf: always a P2P pair (src/fmm.c:438-451, src/remotes.c:228-240)
                 emit_p = 1;
                 const LeafDesc d = a.desc[jm];
@@ -413,7 +410,7 @@ walk_fused_kernel(WalkArgs a, P2PConst pc) {
                 double cj[3], wj[3];
                 load_geom(a.geom, jm, cj, wj);
                 int pruned = 0;
-                if (img != 0) {
+                if (img != 0 || jm >= a.rleaf0) {
                     pruned = pruned_dev(cj, wj, pc.shift[img], a.tc, a.tw, a.cutoff, a.theta, a.longshort);
                     cj[0] += pc.shift[img][0]; cj[1] += pc.shift[img][1]; cj[2] += pc.shift[img][2];
                 }
@@ -498,6 +495,7 @@ static void launch_mode(pn2_ctx *h, const WalkArgs &a, int mode) {
 static void fill_args(pn2_ctx *h, WalkArgs &a) {
     memset(&a, 0, sizeof a);
     a.nleaf = h->nleaf; a.ncell = h->ncell; a.root = h->nleaf;
+    a.rleaf0 = h->ncell; a.rnode0 = h->ncell + h->nrl; a.root_head = h->root_head;
     a.geom = h->geom.p; a.son = h->son.p; a.desc = h->desc.p; a.parent = h->parent.p;
     a.rel = h->rel.p; a.pos = h->pos.p; a.acc = h->acc.p;
     a.cutoff = h->prm.cutoff; a.theta = h->prm.theta; a.longshort = h->prm.longshort; a.maxleaf = h->prm.maxleaf;

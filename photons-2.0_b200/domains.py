@@ -70,23 +70,28 @@ def domain_boxes(P, box):
 def domain_of(pos, P, box):
     """Owner rank of every position: pos > split goes right (src/domains.c:163-296).  pos: torch tensor or numpy (N,3)."""
     splits, _, _, _ = domain_tree(P, box)
-    is_torch = hasattr(pos, "device")
+    is_torch = not isinstance(pos, np.ndarray)
+    n = pos.shape[0]
     if is_torch:
         import torch
-        node = torch.zeros(pos.shape[0], dtype=torch.int64, device=pos.device)
+        node = torch.zeros(n, dtype=torch.int64, device=pos.device)
         spl = torch.tensor(splits, dtype=pos.dtype, device=pos.device)
     else:
-        node = np.zeros(pos.shape[0], np.int64)
+        node = np.zeros(n, np.int64)
         spl = splits
     dim = 0
-    depth = 0
-    while (1 << depth) - 1 < P - 1:          # heap levels that contain internal nodes
-        internal = node < P - 1
-        s = spl[node.clamp(max=2 * P - 2)] if is_torch else spl[np.minimum(node, 2 * P - 2)]
-        right = pos[:, dim] > s
-        nxt = 2 * node + 1 + (right.long() if is_torch else right.astype(np.int64))
-        node = (torch.where(internal, nxt, node) if is_torch else np.where(internal, nxt, node))
+    # walk down the heap until every particle sits on a domain (node >= P - 1); depth <= ceil(log2 P) + 1
+    for _ in range(max(1, P).bit_length() + 1):
+        if is_torch:
+            internal = node < P - 1
+            s = spl[torch.clamp(node, max=2 * P - 2)]
+            nxt = 2 * node + 1 + (pos[:, dim] > s).to(torch.int64)
+            node = torch.where(internal, nxt, node)
+        else:
+            internal = node < P - 1
+            s = spl[np.minimum(node, 2 * P - 2)]
+            nxt = 2 * node + 1 + (pos[:, dim] > s).astype(np.int64)
+            node = np.where(internal, nxt, node)
         dim = (dim + 1) % 3
-        depth += 1
     ml = mostleft(P)
     return (node - ml + P) % P

@@ -31,7 +31,8 @@ EXPORTS = ["pn2_create", "pn2_destroy", "pn2_set_params", "pn2_sync", "pn2_last_
            "pn2_p2p_ext_batch", "pn2_m2l_ext_batch", "pn2_l2l_l2p", "pn2_get_acc", "pn2_zero_acc",
            "pn2_get_multipoles", "pn2_get_locals", "pn2_get_counters", "pn2_force_step", "pn2_force_step_device",
            "pn2_set_comm", "pn2_get_step_info", "pn2_get_order", "pn2_get_cells", "pn2_get_lists", "pn2_fma_peak",
-           "pn2_get_timings", "pn2_launch_count", "pn2_timer_start", "pn2_timer_stop"]
+           "pn2_get_timings", "pn2_launch_count", "pn2_timer_start", "pn2_timer_stop", "pn2_comm_unique_id",
+           "pn2_comm_init_rank", "pn2_step_begin", "pn2_exchange_local", "pn2_step_finish"]
 
 
 class Pn2Error(RuntimeError):
@@ -112,6 +113,11 @@ def lib():
     L.pn2_get_lists.argtypes = [vp, C.c_int, lp, lp, vp, vp, vp]
     L.pn2_fma_peak.argtypes = [vp, C.c_int, dp, dp]
     L.pn2_get_timings.argtypes = [vp, dp]
+    L.pn2_comm_unique_id.argtypes = [vp]
+    L.pn2_comm_init_rank.argtypes = [vp, C.c_int, C.c_int, C.POINTER(Domain), vp]
+    L.pn2_step_begin.argtypes = [vp, vp, C.c_int, C.POINTER(Domain)]
+    L.pn2_exchange_local.argtypes = [C.POINTER(vp), C.c_int]
+    L.pn2_step_finish.argtypes = [vp, vp]
     L.pn2_timer_start.argtypes = [vp, C.c_int]
     L.pn2_timer_stop.argtypes = [vp, C.c_int, dp]
     L.pn2_launch_count.argtypes = [vp]
@@ -247,6 +253,28 @@ class Context:
         arr = (Domain * nranks)(*domains)
         _ck(lib().pn2_set_comm(self.h, rank, nranks, arr, nccl_comm))
 
+    def set_comm_torch(self, rank, nranks, domains):
+        """Create this context's own NCCL communicator; the 128-byte unique id travels over torch.distributed
+        (plumbing), the LET exchange itself is ncclSend/ncclRecv inside libpn2gpu.so."""
+        import torch
+        import torch.distributed as dist
+        buf = (C.c_ubyte * 128)()
+        if rank == 0:
+            _ck(lib().pn2_comm_unique_id(buf))
+        t = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device="cuda")
+        dist.broadcast(t, 0)
+        raw = bytes(t.cpu().tolist())
+        idb = (C.c_ubyte * 128).from_buffer_copy(raw)
+        arr = (Domain * nranks)(*domains)
+        _ck(lib().pn2_comm_init_rank(self.h, rank, nranks, arr, idb))
+
+    def step_begin(self, d_pos_ptr, n, domain):
+        _ck(lib().pn2_step_begin(self.h, d_pos_ptr, n, C.byref(domain)))
+        self.n = n
+
+    def step_finish(self, d_acc_ptr):
+        _ck(lib().pn2_step_finish(self.h, d_acc_ptr))
+
     def force_step(self, pos, domain=None):
         """One whole short-range force evaluation (src/photoNs.c:97-116 without PM); pos (n,3) float64 host."""
         pos = np.ascontiguousarray(pos, np.float64)
@@ -335,3 +363,30 @@ def short_range_force_mode_a(ctx, part_pos, leaf, first_leaf, btree, first_node,
         ctx.m2l_ext_batch(*rm2l)
     ctx.l2l_l2p()
     return ctx.get_acc()
+
+
+def exchange_local(ctxs):
+    """LET exchange between the contexts of one process (ctxs[r] = rank r)."""
+    arr = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+    _ck(lib().pn2_exchange_local(arr, len(ctxs)))
+
+
+def force_step_local_ranks(ctxs, pos_by_rank, domains):
+    """One multi-rank short-range force evaluation with every rank a context of THIS process (device-to-device LET
+    exchange instead of NCCL).  pos_by_rank: list of (n_r, 3) float64 host arrays.  Returns the list of accelerations."""
+    import torch
+    nr = len(ctxs)
+    dpos, dacc = [], []
+    for r in range(nr):
+        ctxs[r].set_comm(r, nr, domains, None)
+        t = torch.from_numpy(np.ascontiguousarray(pos_by_rank[r], np.float64)).cuda()
+        dpos.append(t)
+        dacc.append(torch.zeros_like(t))
+    torch.cuda.synchronize()
+    for r in range(nr):
+        ctxs[r].step_begin(dpos[r].data_ptr(), dpos[r].shape[0], domains[r])
+    exchange_local(ctxs)
+    for r in range(nr):
+        ctxs[r].step_finish(dacc[r].data_ptr())
+        ctxs[r].sync()
+    return [a.cpu().numpy() for a in dacc]

@@ -59,3 +59,43 @@ def sort_pairs(p):
 
 def rms_rel(a, b):
     return float(np.sqrt(((a - b) ** 2).sum() / (b ** 2).sum()))
+
+
+def oracle_step_multirank(oracle, pos_by_rank, boxes, direct0s, prm):
+    """Multi-rank force evaluation with the oracle's reference-pinned walkers / operators on Mode-B trees:
+    per rank local walk; then for every displacement (27 if periodic) and every sender the tree of the sender
+    pruned against the receiver's box (src/fmm.c:1021-1045, src/remotes.c:684-751).  boxes[r] = (lo, hi).
+    Returns per-rank acc (input order of pos_by_rank[r]) and interaction counts."""
+    P = len(pos_by_rank)
+    trees, accs, nints = [], [], []
+    for r in range(P):
+        t = oracle.TreeB(pos_by_rank[r], prm.maxleaf, boxes[r][0], boxes[r][1], direct0=direct0s[r])
+        t.upward(prm.mass)
+        trees.append(t)
+    for r in range(P):
+        t = trees[r]
+        acc = np.zeros((t.n, 3))
+        n0 = t.first_leaf
+        lf_np = t.leaves()["npart"]
+        ps, pt, ms, mt = t.walk_local(prm)
+        t.eval_p2p(prm, ps, pt, acc)
+        t.eval_m2l(prm, ms, mt)
+        nint = int((lf_np[ps - n0].astype(np.int64) * lf_np[pt - n0]).sum() - lf_np[pt[ps == pt] - n0].sum())
+        lo, hi = np.asarray(boxes[r][0], float), np.asarray(boxes[r][1], float)
+        tc, tw = 0.5 * (hi + lo), hi - lo
+        shifts = [(0.0, 0.0, 0.0)] + (image_shifts(prm.box) if prm.periodic else [])
+        for k, sh in enumerate(shifts):
+            for s in range(P):
+                if k == 0 and s == r:
+                    continue
+                lt = trees[s].let_pack(prm, tc, tw, sh)
+                rps, rpt, rms, rmt = t.walk_remote(lt, prm)
+                t.eval_p2p_remote(lt, prm, rps, rpt, acc)
+                t.eval_m2l_remote(lt, prm, rms, rmt)
+                nint += int((lt.arrays()["npart"][rps].astype(np.int64) * lf_np[rpt - n0]).sum())
+        t.downward(acc)
+        out = np.zeros_like(acc)
+        out[t.ids] = acc
+        accs.append(out)
+        nints.append(nint)
+    return accs, nints

@@ -1,0 +1,69 @@
+"""CPU tests of the host-side multi-rank logic: the domain geometry of photons-2.0_b200/domains.py against the oracle
+(src/domains.c:399-472, src/toptree.c:150-181, src/initial.c:199-223), and a world_size-2 gloo run of the
+partitioning + id-broadcast plumbing the multi-GPU bench uses."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("P", [1, 2, 3, 4, 5, 8])
+def test_domain_boxes_and_owner_match_oracle(pn2, oracle, demo_pos, P):
+    import domains
+    box = 100000.0
+    dc, dw, dstart, splits = oracle.domain_boxes(P, box)
+    doms = domains.domain_boxes(P, box)
+    for r in range(P):
+        np.testing.assert_array_equal(np.array(doms[r].lo), dc[r] - 0.5 * dw[r])
+        np.testing.assert_array_equal(np.array(doms[r].hi), dc[r] + 0.5 * dw[r])
+        assert doms[r].direct0 == dstart[r]
+    import ctypes as C
+    L = oracle.lib()
+    pos = demo_pos[::16]
+    own = domains.domain_of(pos, P, box)
+    ref = np.array([L.pno_domain_of(pos[i].ctypes.data_as(C.POINTER(C.c_double)), P, splits.ctypes.data_as(C.POINTER(C.c_double)))
+                    for i in range(len(pos))])
+    np.testing.assert_array_equal(own, ref)
+    import torch
+    own_t = domains.domain_of(torch.from_numpy(pos), P, box).numpy()
+    np.testing.assert_array_equal(own_t, ref)
+
+
+def test_gloo_two_ranks_partition():
+    """world_size 2 over gloo: both ranks generate the same synthetic set, keep their own domain, and agree on counts."""
+    code = r'''
+import os, sys
+sys.path.insert(0, os.path.join(ROOT, "photons-2.0_b200"))
+import torch, torch.distributed as dist
+import numpy as np
+import domains, synthetic
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+pos = synthetic.lcdm_like(16, device="cpu")
+own = domains.domain_of(pos, world, synthetic.BOX)
+mine = pos[own == rank]
+doms = domains.domain_boxes(world, synthetic.BOX)
+lo, hi = np.array(doms[rank].lo), np.array(doms[rank].hi)
+assert bool(((mine.numpy() >= lo) & (mine.numpy() <= hi)).all())
+cnt = torch.tensor([mine.shape[0]])
+dist.all_reduce(cnt)
+assert int(cnt) == 16 ** 3, int(cnt)
+# the 128-byte id broadcast used for the NCCL communicator
+t = torch.arange(128, dtype=torch.uint8) if rank == 0 else torch.zeros(128, dtype=torch.uint8)
+dist.broadcast(t, 0)
+assert int(t.sum()) == sum(range(128))
+dist.destroy_process_group()
+print("ok", rank)
+'''.replace("ROOT", repr(ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29613")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29613", "-c", code] if False else
+                       [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29613", "--no-python", sys.executable, "-c", code],
+                       env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("ok") == 2
