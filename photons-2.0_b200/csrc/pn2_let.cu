@@ -17,7 +17,49 @@
 // single-GPU tests use to drive two ranks).
 #include <cub/cub.cuh>
 #include <nccl.h>
+#include <dlfcn.h>
 #include "pn2_common.cuh"
+
+// NCCL is bound at first use with dlopen, not at link time: a process that also imports torch must end up with ONE
+// libnccl.so.2 (torch's bundled 2.28 needs symbols the system 2.27 lacks).  Order: the copy already mapped into the
+// process, $PN2_NCCL_LIB (pn2gpu.py points it at torch's bundled library), the system library.
+namespace {
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *);
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*GroupStart)();
+    ncclResult_t (*GroupEnd)();
+    const char *(*GetErrorString)(ncclResult_t);
+    bool ok = false;
+};
+NcclApi g_nccl;
+bool nccl_load() {
+    if (g_nccl.ok) return true;
+    void *hd = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    const char *env = getenv("PN2_NCCL_LIB");
+    if (!hd && env && *env) hd = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+    if (!hd) hd = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!hd) { pn2_set_error("pn2: cannot load libnccl.so.2: %s", dlerror()); return false; }
+#define BIND(field, sym) *(void **)(&g_nccl.field) = dlsym(hd, sym); if (!g_nccl.field) { pn2_set_error("pn2: libnccl lacks %s", sym); return false; }
+    BIND(GetUniqueId, "ncclGetUniqueId") BIND(CommInitRank, "ncclCommInitRank") BIND(CommDestroy, "ncclCommDestroy")
+    BIND(Send, "ncclSend") BIND(Recv, "ncclRecv") BIND(GroupStart, "ncclGroupStart") BIND(GroupEnd, "ncclGroupEnd")
+    BIND(GetErrorString, "ncclGetErrorString")
+#undef BIND
+    g_nccl.ok = true;
+    return true;
+}
+}  // namespace
+#define ncclGetUniqueId g_nccl.GetUniqueId
+#define ncclCommInitRank g_nccl.CommInitRank
+#define ncclCommDestroy g_nccl.CommDestroy
+#define ncclSend g_nccl.Send
+#define ncclRecv g_nccl.Recv
+#define ncclGroupStart g_nccl.GroupStart
+#define ncclGroupEnd g_nccl.GroupEnd
+#define ncclGetErrorString g_nccl.GetErrorString
 
 struct __align__(16) PackCell {
     double geom[6];
@@ -295,6 +337,7 @@ int pn2_let_exchange_nccl(pn2_ctx *h) {
     L->r_nl.assign(np, 0); L->r_nn.assign(np, 0); L->r_np.assign(np, 0);
     if (np == 0) return PN2_OK;
     if (!h->nccl) { pn2_set_error("pn2: no NCCL communicator (pn2_set_comm / pn2_comm_init_rank)"); return PN2_ERR_STATE; }
+    if (!nccl_load()) return PN2_ERR_NCCL;
     ncclComm_t comm = (ncclComm_t)h->nccl;
     cudaStream_t st = h->stream;
     PN2_TRY(L->cnt_dev.ensure(8 * (size_t)np));
@@ -426,6 +469,7 @@ int pn2_let_unpack(pn2_ctx *h) {
 extern "C" int pn2_comm_unique_id(void *out128) {
     if (!out128) { pn2_set_error("pn2_comm_unique_id: null"); return PN2_ERR_ARG; }
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    if (!nccl_load()) return PN2_ERR_NCCL;
     ncclUniqueId id;
     NCCL_TRY(ncclGetUniqueId(&id));
     memcpy(out128, &id, 128);
@@ -435,6 +479,7 @@ extern "C" int pn2_comm_unique_id(void *out128) {
 extern "C" int pn2_comm_init_rank(pn2_ctx *h, int rank, int nranks, const pn2_domain *all, const void *id128) {
     if (!h || !all || !id128 || nranks < 1 || rank < 0 || rank >= nranks) { pn2_set_error("pn2_comm_init_rank: bad argument"); return PN2_ERR_ARG; }
     CUDA_TRY(cudaSetDevice(h->device));
+    if (!nccl_load()) return PN2_ERR_NCCL;
     ncclUniqueId id;
     memcpy(&id, id128, 128);
     ncclComm_t comm;
@@ -445,6 +490,6 @@ extern "C" int pn2_comm_init_rank(pn2_ctx *h, int rank, int nranks, const pn2_do
 }
 
 void pn2_comm_release(pn2_ctx *h) {
-    if (h->own_comm && h->nccl) ncclCommDestroy((ncclComm_t)h->nccl);
+    if (h->own_comm && h->nccl && g_nccl.ok) ncclCommDestroy((ncclComm_t)h->nccl);
     h->nccl = nullptr; h->own_comm = false;
 }

@@ -85,6 +85,17 @@ def lib():
         return _lib
     if not os.path.exists(LIB_PATH):
         raise Pn2Error(f"{LIB_PATH} is missing: run __graft_entry__.build() (make -C photons-2.0_b200/csrc)")
+    if "PN2_NCCL_LIB" not in os.environ:
+        # one libnccl per process: prefer the copy bundled with torch (see csrc/pn2_let.cu)
+        try:
+            import importlib.util
+            spec = importlib.util.find_spec("nvidia.nccl")
+            if spec and spec.submodule_search_locations:
+                cand = os.path.join(list(spec.submodule_search_locations)[0], "lib", "libnccl.so.2")
+                if os.path.exists(cand):
+                    os.environ["PN2_NCCL_LIB"] = cand
+        except Exception:
+            pass
     L = C.CDLL(LIB_PATH)
     vp, dp, ip, lp = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_long)
     L.pn2_last_error.restype = C.c_char_p
