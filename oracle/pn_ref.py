@@ -13,6 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_DIR = os.path.join(HERE, "_ref")
 REF_EXE = os.path.join(REF_DIR, "ref_fmm")
 REF_LIB = os.path.join(REF_DIR, "libphotons_ref.so")
+REF_EXE_GPU = os.path.join(REF_DIR, "ref_fmm_gpu")   # the same reference with its task batches routed to libpn2gpu.so
 
 NMULTI = 20
 # struct layouts of the reference (inc/typesdef.h:25-57, inc/photoNs.h:177-189,285-291); sizes probed: SURVEY.md 8
@@ -98,10 +99,11 @@ def _parse_rank(path):
 
 
 def run_reference(pos, box, nside, mass, maxleaf=8, theta=0.4, split=-1.0, soft=-1.0, nranks=1, capture=0,
-                  repeat=1, workdir=None, timeout=3600):
+                  repeat=1, workdir=None, timeout=3600, gpu=False, env_extra=None):
     """Run one short-range force evaluation of the unmodified reference on `pos` (N x 3 float64, in
     [0, box)) at `nranks` ranks of the fork/socketpair mini-MPI.  Returns a list with one dict per rank."""
-    if not available():
+    exe = REF_EXE_GPU if gpu else REF_EXE
+    if not os.path.exists(exe):
         raise RuntimeError("oracle/_ref/ref_fmm is not built (run `make -C oracle ref` where /root/reference exists)")
     pos = np.ascontiguousarray(pos, dtype=np.float64)
     n = pos.shape[0]
@@ -114,7 +116,8 @@ def run_reference(pos, box, nside, mass, maxleaf=8, theta=0.4, split=-1.0, soft=
         xfile = os.path.join(td, "pos.f64")
         pos.tofile(xfile)
         env = dict(os.environ, PN_SHIM_NP=str(nranks))
-        res = subprocess.run([REF_EXE, pfile, xfile, os.path.join(td, "out")], env=env, cwd=td,
+        env.update(env_extra or {})
+        res = subprocess.run([exe, pfile, xfile, os.path.join(td, "out")], env=env, cwd=td,
                              capture_output=True, text=True, timeout=timeout)
         if res.returncode != 0:
             raise RuntimeError(f"ref_fmm failed rc={res.returncode}\n{res.stdout[-2000:]}\n{res.stderr[-2000:]}")

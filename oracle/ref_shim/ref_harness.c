@@ -24,6 +24,9 @@
 #include "domains.h"
 #include "initial.h"
 #include "pn_capture.h"
+#ifdef PN2_GPU_GLUE
+#include "pn2_fmm_glue.h"
+#endif
 #include <string.h>
 #include <sys/time.h>
 
@@ -129,10 +132,16 @@ int pn_ref_run(const double *pos, const PnRefParams *p, const char *outprefix) {
         fmm_construct();
         double t1 = wall();
         fmm_prepare();
+#ifdef PN2_GPU_GLUE
+        pn2_glue_begin_step();          /* drop-in build: task batches go to libpn2gpu.so */
+#endif
         double t2 = wall();
         fmm_task();
         double t3 = wall();
         fmm_ext();
+#ifdef PN2_GPU_GLUE
+        pn2_glue_end_step();
+#endif
         MPI_Barrier(MPI_COMM_WORLD);
         double t4 = wall();
         t_construct += t1 - t0; t_prepare += t2 - t1; t_task += t3 - t2; t_ext += t4 - t3; t_total += t4 - t0;
