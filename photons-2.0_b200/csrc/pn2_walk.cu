@@ -319,27 +319,32 @@ walk_fused_kernel(WalkArgs a, P2PConst pc) {
 
     // ---- drain entries of the source queue through the staged P2P pipeline ----
     int qhead = 0, qtail = 0, buf = 0;
-    auto load_stage = [&](int pos_, int limit) -> float4 {
-        float4 p = make_float4(PN2_PAD_COORD, PN2_PAD_COORD, PN2_PAD_COORD, 0.f);
+    // stage loader, split in two so that the global load stays in flight during the previous stage's arithmetic:
+    // issue() starts the LDG of this lane's source particle and keeps the leaf's centre offset; finish() adds the
+    // offset when the value is finally stored to shared memory.
+    float4 ld_r = make_float4(0.f, 0.f, 0.f, 0.f);
+    float ld_dx = 0.f, ld_dy = 0.f, ld_dz = 0.f;
+    auto issue = [&](int pos_, int limit) {
+        ld_r = make_float4(PN2_PAD_COORD, PN2_PAD_COORD, PN2_PAD_COORD, 0.f);
+        ld_dx = ld_dy = ld_dz = 0.f;
         int idx = pos_ + q;
         if (idx < limit) {
             const SrcEnt *e = &srcq[idx & (SRCQ_CAP - 1)];
             const int4 h4 = *reinterpret_cast<const int4 *>(e);           // first, npart, tag, dx
             if (j < h4.y) {
                 const float2 d2 = *reinterpret_cast<const float2 *>(&e->dy);
-                float4 r = a.rel[h4.x + j];
-                p = make_float4(r.x + __int_as_float(h4.w), r.y + d2.x, r.z + d2.y, 1.f);
+                ld_r = a.rel[h4.x + j];
+                ld_dx = __int_as_float(h4.w); ld_dy = d2.x; ld_dz = d2.y;
             }
         }
-        return p;
     };
     auto drain = [&](int limit) {          // consumes [qhead, limit)
         if (MODE == 0) {
-            float4 pnext = load_stage(qhead, limit);
+            issue(qhead, limit);
             for (int base = qhead; base < limit; base += NSL) {
-                s_stage[wib][buf][q * ST::ROW + j] = pnext;
+                s_stage[wib][buf][q * ST::ROW + j] = make_float4(ld_r.x + ld_dx, ld_r.y + ld_dy, ld_r.z + ld_dz, ld_r.w);
                 __syncwarp();
-                if (base + NSL < limit) pnext = load_stage(base + NSL, limit);
+                if (base + NSL < limit) issue(base + NSL, limit);
                 const float4 *row = &s_stage[wib][buf][q * ST::ROW];
                 if (pc.longshort) {
 #pragma unroll

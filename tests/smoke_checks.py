@@ -48,7 +48,35 @@ def mode_a_small(pn2, oracle, precision):
     return rms_rel(out, g["acc"]), launches
 
 
+def mode_b_small(pn2, oracle, precision):
+    """Device-built tree + lists + images + operators on N = 4096, against the oracle evaluated on the device's own
+    tree (bit-exact tree check included) and against the reference's golden accelerations."""
+    from modeb_check import oracle_step_on_tree
+    g = np.load(os.path.join(GOLDEN, "small_t12_np1.npz"))
+    pos = np.load(os.path.join(GOLDEN, "demo_pos_f32.npy")).astype(np.float64)[::8].copy()
+    box = float(g["box"])
+    prm_o = oracle.make_params(box, int(g["nside"]), len(pos), float(g["mass"]), theta=float(g["theta"]))
+    ctx = pn2.Context(pn2.Params(box, prm_o.rs, prm_o.cutoff, prm_o.soft, prm_o.theta, prm_o.mass, 8, 1, 1, precision))
+    acc = ctx.force_step(pos)
+    tb = oracle.TreeB(pos, 8, [0, 0, 0], [box] * 3)
+    assert np.array_equal(ctx.get_order(), tb.ids), "device tree order differs from the oracle restatement"
+    ref = oracle_step_on_tree(oracle, tb, prm_o, np.array([0.5 * box] * 3), np.array([box] * 3))
+    ref_acc = np.zeros_like(acc)
+    ref_acc[tb.ids] = ref["acc"]
+    info = ctx.step_info()
+    assert info["n_interactions"] == ref["nint"], "device lists differ from the oracle's"
+    launches = ctx.launch_count()
+    ctx.close()
+    return rms_rel(acc, ref_acc), rms_rel(acc, g["acc"]), launches
+
+
 def run(pn2, oracle, np_, verbose=False):
+    for precision, tol in ((pn2.FP64, 1e-6), (pn2.FP32, 1e-4)):
+        e1, e2, launches = mode_b_small(pn2, oracle, precision)
+        if verbose:
+            print(f"smoke: Mode B N=4096 precision={'FP64' if precision == 0 else 'FP32'} rms rel err vs oracle {e1:.3e}, "
+                  f"vs reference golden {e2:.3e} ({launches} kernel launches)")
+        assert e1 < tol and e2 < tol, (precision, e1, e2)
     for precision, tol in ((pn2.FP64, 1e-6), (pn2.FP32, 1e-4)):
         err, launches = mode_a_small(pn2, oracle, precision)
         if verbose:
