@@ -307,7 +307,9 @@ def main():
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("walk_fused_dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            # ncu capture of a smaller launch: scale the measured DRAM bytes by the launch's interaction count
+            traffic = tj["walk_fused_dram_bytes_per_launch"] / tj["interactions_per_launch"] * (nint_total / world)
         except Exception:
             traffic = None
     out = {"metric": METRIC, "value": pps, "unit": "particles/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

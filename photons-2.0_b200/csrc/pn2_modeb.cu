@@ -174,9 +174,9 @@ extern "C" int pn2_force_step(pn2_ctx *h, const double *pos, size_t pos_stride, 
 
 extern "C" int pn2_set_comm(pn2_ctx *h, int rank, int nranks, const pn2_domain *all, void *comm) {
     if (!h || nranks < 1 || rank < 0 || rank >= nranks || !all) { pn2_set_error("pn2_set_comm: bad argument"); return PN2_ERR_ARG; }
-    h->rank = rank; h->nranks = nranks; h->nccl = comm;
+    h->rank = rank; h->nranks = nranks;
+    if (comm) { h->nccl = comm; h->own_comm = false; }      // NULL keeps the communicator already attached
     h->all_dom.assign(all, all + nranks);
-    h->own_comm = false;
     return PN2_OK;
 }
 
