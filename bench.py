@@ -29,6 +29,7 @@ import numpy as np  # noqa: E402
 
 OPS_PER_INTERACTION = 24          # FMA-pipe ops of the P2P inner loop
 METRIC = "short-range force: particles/s per force step"
+_OUT = sys.stdout
 
 
 def parse():
@@ -168,7 +169,7 @@ def run_reference_arm(args):
            "cpu_baseline": {"value": pps, "unit": "particles/s", "cores": r["cores"], "kind": r["kind"], "sample": sample},
            "e2e": {"value": pps, "unit": "particles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0, "wall_s": wall}
-    print(json.dumps(out), flush=True)
+    print(json.dumps(out), file=_OUT, flush=True)
 
 
 def workload_config(args, ngpu):
@@ -182,6 +183,10 @@ def workload_config(args, ngpu):
 
 def main():
     args = parse()
+    # stdout carries exactly ONE JSON line: anything libraries print to fd 1 (e.g. "NCCL version ...") goes to stderr
+    global _OUT
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference_arm(args)
     import torch
@@ -343,7 +348,7 @@ def main():
                                    "p2p_ginteractions_per_s": r["ips"] / 1e9}
         except Exception as ex:  # the bench line must still be printed
             out["cpu_baseline"] = {"value": None, "unit": "particles/s", "cores": cores, "kind": "unavailable", "sample": repr(ex)[:300]}
-    print(json.dumps(out), flush=True)
+    print(json.dumps(out), file=_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
