@@ -809,10 +809,12 @@ void pno_force(const double *pos_in, int n, int P, const pno_params *prm, double
 /* ------------------------------------------------------------------------------------------
  * Mode B tree: CPU restatement of the DEVICE builder (photons-2.0_b200/csrc/pn2_tree.cu).
  * Same tree definition as src/fmm.c:30-264 (mean split, cycling direction, <= MAXLEAF -> leaf, boxes
- * cut by the ancestors' splits) but built level by level: Morton pre-sort (21 bits per dimension of
- * the domain box, stable), the mean from an exact integer sum of coordinates quantised to
- * 2^-e (extent * 2^e < 2^36), stable partition "x > split goes right", breadth-first ids (per level:
- * nodes in range order, son 0 before son 1).  Everything here must match the device bit for bit.
+ * cut by the ancestors' splits) but built level by level and in INTEGER arithmetic:
+ *   q_d = trunc((x_d - lo_d) * 2^(32-e)) (uint32, 2^e > largest box extent); Morton pre-sort on the top
+ *   21 bits of each q (stable); a particle goes right iff q * count > sum(q) over its node (exact 64-bit),
+ *   all of them right if count < 2 (src/fmm.c:33-36); stable partition; split = lo + (sum/count) * 2^-(32-e);
+ *   breadth-first ids (per level: nodes in range order, son 0 before son 1).
+ * Everything here must match the device bit for bit.
  * ------------------------------------------------------------------------------------------ */
 static unsigned long long spread21(unsigned long long v) {
     v &= 0x1fffffULL;
@@ -822,6 +824,12 @@ static unsigned long long spread21(unsigned long long v) {
     v = (v | v << 4) & 0x10c30c30c30c30c3ULL;
     v = (v | v << 2) & 0x1249249249249249ULL;
     return v;
+}
+static unsigned quant32(double x, double lo, double S) {
+    double f = (x - lo) * S;
+    if (!(f > 0.0)) return 0u;
+    if (f >= 4294967295.0) return 4294967295u;
+    return (unsigned)f;
 }
 typedef struct { unsigned long long key; int idx; } mkey;
 static int mkey_cmp(const void *a, const void *b) {
@@ -838,29 +846,25 @@ pno_tree *pno_treeB_build(const double *pos_in, int n, int maxleaf, int direct0,
     t->first_leaf = t->last_leaf = n;
     t->first_node = n; t->last_node = n - 1;
     if (n == 0) return t;
-    double ext[3], sc[3];
-    for (int d = 0; d < 3; d++) { ext[d] = br[d] - bl[d]; sc[d] = 2097152.0 / ext[d]; }
-    mkey *mk = (mkey *)malloc(n*sizeof(mkey));
-    for (int i = 0; i < n; i++) {
-        long long c[3];
-        for (int d = 0; d < 3; d++) {
-            double f = (pos_in[3*i+d] - bl[d]) * sc[d];
-            c[d] = f > 0.0 ? (long long)f : 0;
-            if (c[d] > 0x1fffff) c[d] = 0x1fffff;
-        }
-        mk[i].key = (spread21((unsigned long long)c[0]) << 2) | (spread21((unsigned long long)c[1]) << 1) | spread21((unsigned long long)c[2]);
-        mk[i].idx = i;
-    }
-    qsort(mk, n, sizeof(mkey), mkey_cmp);
-    double *pa = (double *)malloc(3*(size_t)n*sizeof(double)), *pb = (double *)malloc(3*(size_t)n*sizeof(double));
-    int *ia = (int *)malloc(n*sizeof(int)), *ib = (int *)malloc(n*sizeof(int));
-    for (int i = 0; i < n; i++) { ia[i] = mk[i].idx; for (int d = 0; d < 3; d++) pa[3*i+d] = pos_in[3*(size_t)mk[i].idx+d]; }
-    free(mk);
+    double ext[3];
+    for (int d = 0; d < 3; d++) ext[d] = br[d] - bl[d];
     double emax = ext[0] > ext[1] ? ext[0] : ext[1];
     if (ext[2] > emax) emax = ext[2];
     int e2 = 0;
     frexp(emax, &e2);
-    const double S = ldexp(1.0, 36 - e2), invS = ldexp(1.0, e2 - 36);
+    const double S = ldexp(1.0, 32 - e2), invS = ldexp(1.0, e2 - 32);
+    unsigned *q0 = (unsigned *)malloc(3*(size_t)n*sizeof(unsigned));
+    mkey *mk = (mkey *)malloc(n*sizeof(mkey));
+    for (int i = 0; i < n; i++) {
+        for (int d = 0; d < 3; d++) q0[3*(size_t)i+d] = quant32(pos_in[3*(size_t)i+d], bl[d], S);
+        mk[i].key = (spread21(q0[3*(size_t)i] >> 11) << 2) | (spread21(q0[3*(size_t)i+1] >> 11) << 1) | spread21(q0[3*(size_t)i+2] >> 11);
+        mk[i].idx = i;
+    }
+    qsort(mk, n, sizeof(mkey), mkey_cmp);
+    unsigned *qa = (unsigned *)malloc(3*(size_t)n*sizeof(unsigned)), *qb = (unsigned *)malloc(3*(size_t)n*sizeof(unsigned));
+    int *ia = (int *)malloc(n*sizeof(int)), *ib = (int *)malloc(n*sizeof(int));
+    for (int i = 0; i < n; i++) { ia[i] = mk[i].idx; for (int d = 0; d < 3; d++) qa[3*(size_t)i+d] = q0[3*(size_t)mk[i].idx+d]; }
+    free(mk); free(q0);
     /* growable node / leaf records */
     int ncap = 1024, lcap = 1024, nn = 1, nl = 0;
     int *ns = (int *)malloc(ncap*sizeof(int)), *nc = (int *)malloc(ncap*sizeof(int)), *nson = (int *)malloc(2*ncap*sizeof(int));
@@ -877,21 +881,21 @@ pno_tree *pno_treeB_build(const double *pos_in, int n, int maxleaf, int direct0,
         for (int k = 0; k < cnt; k++) {
             int nd = node0 + k, a = ns[nd], c = nc[nd];
             unsigned long long sum = 0;
-            for (int i = a; i < a + c; i++) {
-                double f = (pa[3*(size_t)i+dir] - lo) * S;
-                sum += f > 0.0 ? (unsigned long long)f : 0ULL;
-            }
+            for (int i = a; i < a + c; i++) sum += qa[3*(size_t)i+dir];
             double m = (double)sum / (double)c;
             double split = lo + m * invS;
             nsp[nd] = split;
-            /* stable partition into pb */
+            /* stable partition into qb / ib */
             int nleft = 0;
-            for (int i = a; i < a + c; i++) { int fl = (c < 2) ? 1 : (pa[3*(size_t)i+dir] > split); if (!fl) nleft++; }
+            for (int i = a; i < a + c; i++) {
+                int fl = (c < 2) ? 1 : ((unsigned long long)qa[3*(size_t)i+dir] * (unsigned long long)c > sum);
+                if (!fl) nleft++;
+            }
             int pl = a, pr = a + nleft;
             for (int i = a; i < a + c; i++) {
-                int fl = (c < 2) ? 1 : (pa[3*(size_t)i+dir] > split);
+                int fl = (c < 2) ? 1 : ((unsigned long long)qa[3*(size_t)i+dir] * (unsigned long long)c > sum);
                 int dst = fl ? pr++ : pl++;
-                pb[3*(size_t)dst] = pa[3*(size_t)i]; pb[3*(size_t)dst+1] = pa[3*(size_t)i+1]; pb[3*(size_t)dst+2] = pa[3*(size_t)i+2];
+                qb[3*(size_t)dst] = qa[3*(size_t)i]; qb[3*(size_t)dst+1] = qa[3*(size_t)i+1]; qb[3*(size_t)dst+2] = qa[3*(size_t)i+2];
                 ib[dst] = ia[i];
             }
             int cn[2] = {nleft, c - nleft}, st[2] = {a, a + nleft};
@@ -915,15 +919,11 @@ pno_tree *pno_treeB_build(const double *pos_in, int n, int maxleaf, int direct0,
                 }
             }
         }
-        /* particles of finished leaves do not move */
-        /* (pb was only written inside this level's node ranges) */
-        {
-            /* copy back the ranges of this level's nodes */
-            for (int k = 0; k < cnt; k++) {
-                int nd = node0 + k, a = ns[nd], c = nc[nd];
-                memcpy(pa + 3*(size_t)a, pb + 3*(size_t)a, 3*(size_t)c*sizeof(double));
-                memcpy(ia + a, ib + a, c*sizeof(int));
-            }
+        /* particles of finished leaves do not move: copy back only this level's node ranges */
+        for (int k = 0; k < cnt; k++) {
+            int nd = node0 + k, a = ns[nd], c = nc[nd];
+            memcpy(qa + 3*(size_t)a, qb + 3*(size_t)a, 3*(size_t)c*sizeof(unsigned));
+            memcpy(ia + a, ib + a, c*sizeof(int));
         }
         node0 = next0; cnt = nnext; nn = next0 + nnext; level++;
         if (level > 200) { fprintf(stderr, "pn_oracle: treeB deeper than 200 levels\n"); exit(3); }
@@ -957,8 +957,8 @@ pno_tree *pno_treeB_build(const double *pos_in, int n, int maxleaf, int direct0,
             t->nd_son[2*k+s] = ch >= 0 ? t->first_node + ch : t->first_leaf + (-(ch + 2));
         }
     }
-    if (pos_out) memcpy(pos_out, pa, 3*(size_t)n*sizeof(double));
+    if (pos_out) for (int i = 0; i < n; i++) for (int d = 0; d < 3; d++) pos_out[3*(size_t)i+d] = pos_in[3*(size_t)ia[i]+d];
     if (order) memcpy(order, ia, n*sizeof(int));
-    free(pa); free(pb); free(ia); free(ib); free(ns); free(nc); free(nson); free(nbox); free(nsp); free(ls); free(lc); free(lbox);
+    free(qa); free(qb); free(ia); free(ib); free(ns); free(nc); free(nson); free(nbox); free(nsp); free(ls); free(lc); free(lbox);
     return t;
 }

@@ -123,7 +123,9 @@ struct pn2_ctx {
     // ---- Mode B (device-built tree / lists) ----
     DBuf<int> order;                 // [n] caller index of the k-th particle in tree order
     DBuf<int> parent, depth;         // [ncell]
-    DBuf<double> b_pos2;             // ping-pong of pos during the build
+    DBuf<uint4> b_pay, b_pay2;       // build payload {qx, qy, qz, caller index}, ping-pong
+    DBuf<unsigned> b_qc, b_qc2;      // the current level's key
+    DBuf<unsigned long long> n_sum;  // per-node coordinate sums
     DBuf<int> b_idx2, b_seg, b_seg2;
     DBuf<unsigned long long> b_q;    // quantised coordinates / their scan, morton keys
     DBuf<unsigned long long> b_key2;

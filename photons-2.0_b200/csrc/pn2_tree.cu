@@ -4,23 +4,22 @@
 // MEAN of the node's particles, direction cycling x->y->z from direct_local_start, a child with
 // <= MAXLEAF particles becomes a leaf, boxes are the domain box cut by the ancestors' splits.  The
 // reference builds it by depth-first recursion with an in-place Hoare partition and a sequential
-// FP64 sum (inherently serial); here it is built LEVEL BY LEVEL over all nodes of a depth at once:
+// FP64 sum (inherently serial); here it is built LEVEL BY LEVEL over all nodes of a depth at once, and
+// entirely in INTEGER arithmetic so that a CPU restatement (oracle: pno_treeB_build) reproduces it bit
+// for bit whatever the summation order:
 //
-//   0. Morton pre-sort: 63-bit keys (21 bits per dimension of the domain box), LSD radix sort.
-//      It fixes the particle order inside every leaf (stable partitions keep Morton order).
-//   per level, direction dir = (direct0 + level) % 3:
-//   1. q_i = trunc((x_i[dir] - lo[dir]) * 2^e) as uint64, exclusive prefix sum over all particles;
-//      a node's coordinate sum is a difference of two prefix values: exact integers, independent of
-//      summation order, so a CPU restatement reproduces every split bit for bit (oracle: pno_treeB_build).
-//   2. split = lo[dir] + (sum / count) * 2^-e;  flag_i = x_i[dir] > split (the reference's "> mean goes right",
-//      src/fmm.c:60-72); exclusive prefix sum of the flags gives every particle its slot in a STABLE
-//      partition of its node's range.
-//   3. children: count <= MAXLEAF -> leaf, else node of the next level; ids are handed out by prefix
-//      sums over the level (breadth-first numbering, deterministic).
-//   4. scatter particles (position, caller index, next node) to the other buffer.
-//
-// All FP64 expressions that decide tree shape use explicit round-to-nearest intrinsics (no FMA
-// contraction) in the order the oracle uses.
+//   0. q_d = trunc((x_d - lo_d) * 2^(32-e)) as uint32 per dimension, 2^e > largest box extent.
+//      Morton pre-sort: 63-bit key from the top 21 bits of each q, LSD radix sort (stable).  It fixes the
+//      particle order inside every leaf (the partitions below are stable).
+//   per level, direction dir = (direct0 + level) % 3, payload per particle = {qx, qy, qz, caller index}:
+//   1. exclusive prefix sum (uint64) of q_dir over all particles: a node's coordinate sum is a difference of two
+//      prefix values -- exact.  split = lo_dir + (sum / count) * 2^-(32-e) (only the boxes use the FP value).
+//   2. flag_i = q_i * count > sum  ("> mean goes right", src/fmm.c:60-72; exact 64-bit products), exclusive
+//      prefix sum of the flags gives every particle its slot in a STABLE partition of its node's range.
+//   3. children: count <= MAXLEAF -> leaf, else node of the next level; ids are handed out by prefix sums over the
+//      level (breadth-first numbering, deterministic).
+//   4. scatter the 16-byte payload, the next node id and the next level's key to the other buffer.
+//   ~80 B of HBM traffic per particle per level; the FP64 positions are gathered once at the end.
 #include <cub/cub.cuh>
 #include "pn2_common.cuh"
 
@@ -37,68 +36,62 @@ __device__ __forceinline__ unsigned long long spread21(unsigned long long v) {
     return v;
 }
 
-// Morton key: cell index floor((x - lo) * (2^21 / (hi - lo))) per dimension, clamped to [0, 2^21)
-__global__ void morton_kernel(int n, const double *__restrict__ pos, double lox, double loy, double loz, double sx,
-                              double sy, double sz, unsigned long long *__restrict__ key, int *__restrict__ idx) {
+__device__ __forceinline__ unsigned quant32(double x, double lo, double S) {
+    double f = __dmul_rn(__dsub_rn(x, lo), S);
+    if (!(f > 0.0)) return 0u;
+    if (f >= 4294967295.0) return 4294967295u;
+    return (unsigned)f;                       // truncation
+}
+
+__global__ void quant_morton_kernel(int n, const double *__restrict__ pos, double lox, double loy, double loz, double S,
+                                    uint4 *__restrict__ pay, unsigned long long *__restrict__ key, int *__restrict__ idx) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    double fx = __dmul_rn(__dsub_rn(pos[3 * (size_t)i], lox), sx);
-    double fy = __dmul_rn(__dsub_rn(pos[3 * (size_t)i + 1], loy), sy);
-    double fz = __dmul_rn(__dsub_rn(pos[3 * (size_t)i + 2], loz), sz);
-    long long ix = fx > 0.0 ? (long long)fx : 0, iy = fy > 0.0 ? (long long)fy : 0, iz = fz > 0.0 ? (long long)fz : 0;
-    if (ix > 0x1fffff) ix = 0x1fffff;
-    if (iy > 0x1fffff) iy = 0x1fffff;
-    if (iz > 0x1fffff) iz = 0x1fffff;
-    key[i] = (spread21((unsigned long long)ix) << 2) | (spread21((unsigned long long)iy) << 1) | spread21((unsigned long long)iz);
+    unsigned qx = quant32(pos[3 * (size_t)i], lox, S), qy = quant32(pos[3 * (size_t)i + 1], loy, S), qz = quant32(pos[3 * (size_t)i + 2], loz, S);
+    pay[i] = make_uint4(qx, qy, qz, (unsigned)i);
+    key[i] = (spread21(qx >> 11) << 2) | (spread21(qy >> 11) << 1) | spread21(qz >> 11);
     idx[i] = i;
 }
 
-__global__ void gather_pos_kernel(int n, const double *__restrict__ pos_in, const int *__restrict__ idx,
-                                  double *__restrict__ pos_out, int *__restrict__ seg) {
+__global__ void gather_pay_kernel(int n, const uint4 *__restrict__ pay_in, const int *__restrict__ idx, int dir,
+                                  uint4 *__restrict__ pay_out, unsigned *__restrict__ qcur, int *__restrict__ seg) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    size_t j = (size_t)idx[i];
-    pos_out[3 * (size_t)i] = pos_in[3 * j];
-    pos_out[3 * (size_t)i + 1] = pos_in[3 * j + 1];
-    pos_out[3 * (size_t)i + 2] = pos_in[3 * j + 2];
+    uint4 p = pay_in[idx[i]];
+    pay_out[i] = p;
+    qcur[i] = dir == 0 ? p.x : (dir == 1 ? p.y : p.z);
     seg[i] = 0;                                          // everyone starts in the root
 }
 
-__global__ void quantize_kernel(int n, const double *__restrict__ pos, const int *__restrict__ seg, int dir, double lo,
-                                double S, unsigned long long *__restrict__ q) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > n) return;
-    unsigned long long v = 0;
-    if (i < n && seg[i] >= 0) {
-        double f = __dmul_rn(__dsub_rn(pos[3 * (size_t)i + dir], lo), S);
-        v = f > 0.0 ? (unsigned long long)f : 0ULL;
+// scan inputs computed on the fly
+struct KeyOf {
+    const unsigned *q; const int *seg; int n;
+    __host__ __device__ unsigned long long operator()(int i) const { return (i < n && seg[i] >= 0) ? (unsigned long long)q[i] : 0ULL; }
+};
+struct FlagOf {
+    const unsigned *q; const int *seg; const unsigned long long *n_sum; const int *n_count; int n;
+    __host__ __device__ int operator()(int i) const {
+        if (i >= n) return 0;
+        int s = seg[i];
+        if (s < 0) return 0;
+        int c = n_count[s];
+        if (c < 2) return 1;                                                 // len < 2: src/fmm.c:33-36
+        return ((unsigned long long)q[i] * (unsigned long long)c > n_sum[s]) ? 1 : 0;
     }
-    q[i] = v;                                            // q[n] = 0: the scan's last slot is the grand total
-}
+};
 
-// one thread per node of the level: split position from the prefix sums
+// one thread per node of the level: coordinate sum and split position
 __global__ void split_kernel(int cnt, int node0, const int *__restrict__ n_start, const int *__restrict__ n_count,
                              const unsigned long long *__restrict__ Sq, double lo, double invS,
-                             double *__restrict__ n_split) {
+                             unsigned long long *__restrict__ n_sum, double *__restrict__ n_split) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= cnt) return;
     int nd = node0 + k;
     int a = n_start[nd], c = n_count[nd];
     unsigned long long sum = Sq[a + c] - Sq[a];
+    n_sum[nd] = sum;
     double m = __ddiv_rn(__ull2double_rn(sum), (double)c);
     n_split[nd] = __dadd_rn(lo, __dmul_rn(m, invS));
-}
-
-__global__ void flag_kernel(int n, const double *__restrict__ pos, const int *__restrict__ seg, int dir,
-                            const double *__restrict__ n_split, const int *__restrict__ n_count, int *__restrict__ f) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > n) return;
-    int v = 0;
-    if (i < n) {
-        int s = seg[i];
-        if (s >= 0) v = (n_count[s] < 2) ? 1 : (pos[3 * (size_t)i + dir] > n_split[s] ? 1 : 0);   // len < 2: src/fmm.c:33-36
-    }
-    f[i] = v;
 }
 
 // per node: how many leaf / node children (packed leaf | node << 32) for the numbering scan
@@ -168,10 +161,9 @@ __global__ void children_kernel(int cnt, int node0, int next_node0, int leaf0, i
     }
 }
 
-__global__ void scatter_kernel(int n, const double *__restrict__ pos, const int *__restrict__ idx, const int *__restrict__ seg,
-                               const int *__restrict__ F, const int *__restrict__ n_start, const int *__restrict__ n_count,
-                               const int *__restrict__ n_son, double *__restrict__ pos_o, int *__restrict__ idx_o,
-                               int *__restrict__ seg_o) {
+__global__ void scatter_kernel(int n, const uint4 *__restrict__ pay, const int *__restrict__ seg, const int *__restrict__ F,
+                               const int *__restrict__ n_start, const int *__restrict__ n_count, const int *__restrict__ n_son,
+                               int next_dir, uint4 *__restrict__ pay_o, int *__restrict__ seg_o, unsigned *__restrict__ q_o) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int s = seg[i];
@@ -184,11 +176,22 @@ __global__ void scatter_kernel(int n, const double *__restrict__ pos, const int 
         int ch = n_son[2 * (size_t)s + fl];
         ns = ch >= 0 ? ch : -1;
     }
-    pos_o[3 * (size_t)np] = pos[3 * (size_t)i];
-    pos_o[3 * (size_t)np + 1] = pos[3 * (size_t)i + 1];
-    pos_o[3 * (size_t)np + 2] = pos[3 * (size_t)i + 2];
-    idx_o[np] = idx[i];
+    uint4 p = pay[i];
+    pay_o[np] = p;
     seg_o[np] = ns;
+    q_o[np] = next_dir == 0 ? p.x : (next_dir == 1 ? p.y : p.z);
+}
+
+// tree-order positions and caller indices from the final payload
+__global__ void finalize_particles_kernel(int n, const uint4 *__restrict__ pay, const double *__restrict__ pos_in,
+                                          double *__restrict__ pos, int *__restrict__ order) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    size_t j = (size_t)pay[i].w;
+    order[i] = (int)j;
+    pos[3 * (size_t)i] = pos_in[3 * j];
+    pos[3 * (size_t)i + 1] = pos_in[3 * j + 1];
+    pos[3 * (size_t)i + 2] = pos_in[3 * j + 2];
 }
 
 // cells: leaves 0..nleaf-1, nodes nleaf..; geometry as center_kdtree computes it (src/fmm.c:126-131)
@@ -237,12 +240,15 @@ int pn2_tree_build_device(pn2_ctx *h, const double *d_pos_in, int n, const pn2_d
     h->n = n;
     h->dom = *dom;
     h->nleaf = h->nnode = h->ncell = h->nlevel = 0;
+    h->nrl = h->nrn = h->nrp = 0;
     h->level_off.assign(1, 0);
-    PN2_TRY(h->pos.ensure(3 * (size_t)n + 3)); PN2_TRY(h->b_pos2.ensure(3 * (size_t)n + 3));
+    PN2_TRY(h->pos.ensure(3 * (size_t)n + 3));
     PN2_TRY(h->acc.ensure(3 * (size_t)n + 3)); PN2_TRY(h->rel.ensure((size_t)n + 1));
     PN2_TRY(h->order.ensure(n + 1)); PN2_TRY(h->b_idx2.ensure(n + 1));
     PN2_TRY(h->b_seg.ensure(n + 1)); PN2_TRY(h->b_seg2.ensure(n + 1));
     PN2_TRY(h->b_q.ensure(n + 2)); PN2_TRY(h->b_key2.ensure(n + 2)); PN2_TRY(h->b_f.ensure(n + 2));
+    PN2_TRY(h->b_pay.ensure((size_t)n + 1)); PN2_TRY(h->b_pay2.ensure((size_t)n + 1));
+    PN2_TRY(h->b_qc.ensure((size_t)n + 1)); PN2_TRY(h->b_qc2.ensure((size_t)n + 1));
     PN2_TRY(h->b_scal.ensure(16));
     if (n == 0) return PN2_OK;
     // capacities: a full binary tree, nnode = nleaf - 1; leaves hold >= 1 particle unless coordinates coincide
@@ -250,24 +256,37 @@ int pn2_tree_build_device(pn2_ctx *h, const double *d_pos_in, int n, const pn2_d
     if (cap > n + 2) cap = n + 2;
     PN2_TRY(h->n_start.ensure(cap)); PN2_TRY(h->n_count.ensure(cap)); PN2_TRY(h->n_son.ensure(2 * (size_t)cap));
     PN2_TRY(h->n_depth.ensure(cap)); PN2_TRY(h->n_box.ensure(6 * (size_t)cap)); PN2_TRY(h->n_split.ensure(cap));
+    PN2_TRY(h->n_sum.ensure(cap));
     PN2_TRY(h->l_start.ensure(cap)); PN2_TRY(h->l_count.ensure(cap)); PN2_TRY(h->l_box.ensure(6 * (size_t)cap));
 
-    // ---- 0. Morton pre-sort ----
-    double ext[3], sc[3];
-    for (int d = 0; d < 3; d++) { ext[d] = dom->hi[d] - dom->lo[d]; sc[d] = 2097152.0 / ext[d]; }
-    morton_kernel<<<nb(n), TB, 0, st>>>(n, d_pos_in, dom->lo[0], dom->lo[1], dom->lo[2], sc[0], sc[1], sc[2], h->b_q.p, h->b_idx2.p);
+    // quantisation scale: extent * 2^(32-e) < 2^32
+    double ext[3];
+    for (int d = 0; d < 3; d++) ext[d] = dom->hi[d] - dom->lo[d];
+    double emax = ext[0] > ext[1] ? ext[0] : ext[1];
+    if (ext[2] > emax) emax = ext[2];
+    int e2 = 0;
+    frexp(emax, &e2);                    // emax = f * 2^e2, f in [0.5, 1)
+    const double S = ldexp(1.0, 32 - e2), invS = ldexp(1.0, e2 - 32);
+
+    // ---- 0. quantise + Morton pre-sort ----
+    quant_morton_kernel<<<nb(n), TB, 0, st>>>(n, d_pos_in, dom->lo[0], dom->lo[1], dom->lo[2], S, h->b_pay2.p, h->b_q.p, h->b_idx2.p);
+    KeyOf keyf{h->b_qc.p, h->b_seg.p, n};
+    FlagOf flagf{h->b_qc.p, h->b_seg.p, h->n_sum.p, h->n_count.p, n};
+    cub::CountingInputIterator<int> cnt_it(0);
+    cub::TransformInputIterator<unsigned long long, KeyOf, cub::CountingInputIterator<int>> key_it(cnt_it, keyf);
+    cub::TransformInputIterator<int, FlagOf, cub::CountingInputIterator<int>> flag_it(cnt_it, flagf);
     size_t tb = 0, tb2 = 0, tb3 = 0, tb4 = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tb, h->b_q.p, h->b_key2.p, h->b_idx2.p, h->order.p, n, 0, 63, st);
-    cub::DeviceScan::ExclusiveSum(nullptr, tb2, h->b_q.p, h->b_key2.p, n + 1, st);
-    cub::DeviceScan::ExclusiveSum(nullptr, tb3, h->b_f.p, h->b_seg2.p, n + 1, st);
-    cub::DeviceScan::ExclusiveSum(nullptr, tb4, h->b_q.p, h->b_key2.p, cap + 1, st);
+    cub::DeviceScan::ExclusiveSum(nullptr, tb2, key_it, h->b_key2.p, n + 1, st);
+    cub::DeviceScan::ExclusiveSum(nullptr, tb3, flag_it, h->b_f.p, n + 1, st);
+    cub::DeviceScan::ExclusiveSum(nullptr, tb4, h->b_q.p, h->b_q.p, cap + 1, st);
     size_t need = tb;
     if (tb2 > need) need = tb2;
     if (tb3 > need) need = tb3;
     if (tb4 > need) need = tb4;
     PN2_TRY(h->tmp.ensure(need + 16));
     cub::DeviceRadixSort::SortPairs(h->tmp.p, tb, h->b_q.p, h->b_key2.p, h->b_idx2.p, h->order.p, n, 0, 63, st);
-    gather_pos_kernel<<<nb(n), TB, 0, st>>>(n, d_pos_in, h->order.p, h->pos.p, h->b_seg.p);
+    gather_pay_kernel<<<nb(n), TB, 0, st>>>(n, h->b_pay2.p, h->order.p, dom->direct0 % 3, h->b_pay.p, h->b_qc.p, h->b_seg.p);
     h->launches += 3;
 
     // ---- root ----
@@ -283,47 +302,43 @@ int pn2_tree_build_device(pn2_ctx *h, const double *d_pos_in, int n, const pn2_d
         CUDA_TRY(cudaMemsetAsync(h->b_scal.p, 0, 16 * sizeof(int), st));
         CUDA_TRY(cudaStreamSynchronize(st));
     }
-    // quantisation scale: extent * 2^e < 2^36, so a sum over < 2^27 particles stays below 2^63
-    double emax = ext[0] > ext[1] ? ext[0] : ext[1];
-    if (ext[2] > emax) emax = ext[2];
-    int e2 = 0;
-    frexp(emax, &e2);                    // emax = f * 2^e2, f in [0.5, 1)
-    const double S = ldexp(1.0, 36 - e2), invS = ldexp(1.0, e2 - 36);
 
-    double *pc = h->pos.p, *po = h->b_pos2.p;
-    int *ic = h->order.p, *io = h->b_idx2.p, *sg = h->b_seg.p, *so = h->b_seg2.p;
+    uint4 *pc = h->b_pay.p, *po = h->b_pay2.p;
+    unsigned *qc = h->b_qc.p, *qo = h->b_qc2.p;
+    int *sg = h->b_seg.p, *so = h->b_seg2.p;
     int node0 = 0, cnt = 1, nleaf = 0, level = 0;
     std::vector<int> level_off(1, 0);
     while (cnt > 0) {
         if (level > 200) { pn2_set_error("pn2: tree deeper than 200 levels (more than MAXLEAF coincident particles?)"); return PN2_ERR_ARG; }
         int dir = (dom->direct0 + level) % 3;
         double lo = dom->lo[dir];
-        quantize_kernel<<<nb(n + 1), TB, 0, st>>>(n, pc, sg, dir, lo, S, h->b_q.p);
-        cub::DeviceScan::ExclusiveSum(h->tmp.p, tb2, h->b_q.p, h->b_key2.p, n + 1, st);
-        split_kernel<<<nb(cnt), TB, 0, st>>>(cnt, node0, h->n_start.p, h->n_count.p, h->b_key2.p, lo, invS, h->n_split.p);
-        flag_kernel<<<nb(n + 1), TB, 0, st>>>(n, pc, sg, dir, h->n_split.p, h->n_count.p, h->b_f.p);
-        cub::DeviceScan::ExclusiveSum(h->tmp.p, tb3, h->b_f.p, h->b_f.p, n + 1, st);
+        keyf.q = qc; keyf.seg = sg;
+        flagf.q = qc; flagf.seg = sg;
+        cub::TransformInputIterator<unsigned long long, KeyOf, cub::CountingInputIterator<int>> kit(cnt_it, keyf);
+        cub::TransformInputIterator<int, FlagOf, cub::CountingInputIterator<int>> fit(cnt_it, flagf);
+        cub::DeviceScan::ExclusiveSum(h->tmp.p, tb2, kit, h->b_key2.p, n + 1, st);
+        split_kernel<<<nb(cnt), TB, 0, st>>>(cnt, node0, h->n_start.p, h->n_count.p, h->b_key2.p, lo, invS, h->n_sum.p, h->n_split.p);
+        cub::DeviceScan::ExclusiveSum(h->tmp.p, tb3, fit, h->b_f.p, n + 1, st);
         childcount_kernel<<<nb(cnt + 1), TB, 0, st>>>(cnt, node0, h->n_start.p, h->n_count.p, h->b_f.p, maxleaf, h->b_q.p);
         cub::DeviceScan::ExclusiveSum(h->tmp.p, tb4, h->b_q.p, h->b_q.p, cnt + 1, st);
         children_kernel<<<nb(cnt), TB, 0, st>>>(cnt, node0, node0 + cnt, nleaf, dir, level, maxleaf, h->n_start.p, h->n_count.p,
                                                 h->n_son.p, h->n_depth.p, h->n_box.p, h->n_split.p, h->l_start.p,
                                                 h->l_count.p, h->l_box.p, h->b_f.p, h->b_q.p, cap, cap, h->b_scal.p);
-        scatter_kernel<<<nb(n), TB, 0, st>>>(n, pc, ic, sg, h->b_f.p, h->n_start.p, h->n_count.p, h->n_son.p, po, io, so);
-        h->launches += 9;
+        scatter_kernel<<<nb(n), TB, 0, st>>>(n, pc, sg, h->b_f.p, h->n_start.p, h->n_count.p, h->n_son.p, (dir + 1) % 3, po, so, qo);
+        h->launches += 7;
         int hs[4];
         CUDA_TRY(cudaMemcpyAsync(hs, h->b_scal.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
         if (hs[3]) { pn2_set_error("pn2: tree capacity %d exceeded (degenerate particle distribution)", cap); return PN2_ERR_NOMEM; }
-        std::swap(pc, po); std::swap(ic, io); std::swap(sg, so);
+        std::swap(pc, po); std::swap(qc, qo); std::swap(sg, so);
         node0 += cnt;
         level_off.push_back(node0);
         cnt = hs[0];
         nleaf = hs[1];
         level++;
     }
-    // make h->pos / h->order the final buffers
-    if (pc != h->pos.p) { std::swap(h->pos, h->b_pos2); }
-    if (ic != h->order.p) { std::swap(h->order, h->b_idx2); }
+    finalize_particles_kernel<<<nb(n), TB, 0, st>>>(n, pc, d_pos_in, h->pos.p, h->order.p);
+    h->launches++;
     const int nnode = node0;
     if ((size_t)nleaf + nnode >= (1u << PN2_IMG_SHIFT)) { pn2_set_error("pn2: more than 2^26 cells on one device"); return PN2_ERR_ARG; }
     h->nleaf = nleaf; h->nnode = nnode; h->ncell = nleaf + nnode; h->nlevel = level;

@@ -27,7 +27,7 @@
 #define SRCQ_CAP 64
 #define OBUF_CAP 256              // per-warp staging of O(im) before it is flushed to a span
 #ifndef LEAF_MIN_BLOCKS
-#define LEAF_MIN_BLOCKS 7          // register cap of the leaf kernel (72 regs, 28 warps/SM): best of 5..8 measured at 256^3
+#define LEAF_MIN_BLOCKS 8          // register cap of the leaf kernel (64 regs, 32 warps/SM): best of 5..8 measured at 256^3
 #endif
 
 struct WalkArgs {
@@ -151,7 +151,10 @@ __device__ __forceinline__ void emit_m2l_pairs(const WalkArgs &a, int lane, unsi
 // ------------------------------------------------------------------------------------------------
 // Pass 1: one warp per sink NODE of one level: F(im) -> M2L pairs + O(im)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(WALK_WARPS * 32) frontier_node_kernel(WalkArgs a, P2PConst pc) {
+#ifndef NODE_MIN_BLOCKS
+#define NODE_MIN_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(WALK_WARPS * 32, NODE_MIN_BLOCKS) frontier_node_kernel(WalkArgs a, P2PConst pc) {
     __shared__ unsigned s_stack[WALK_WARPS][STACK_CAP];
     __shared__ unsigned s_obuf[WALK_WARPS][OBUF_CAP];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
