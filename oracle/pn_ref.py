@@ -13,6 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_DIR = os.path.join(HERE, "_ref")
 REF_EXE = os.path.join(REF_DIR, "ref_fmm")
 REF_LIB = os.path.join(REF_DIR, "libphotons_ref.so")
+REF_EXE_OPEN = os.path.join(REF_DIR, "ref_fmm_open")   # built without -DPERIODIC_CONDITION -DLONGSHORT
 REF_EXE_GPU = os.path.join(REF_DIR, "ref_fmm_gpu")   # the same reference with its task batches routed to libpn2gpu.so
 
 NMULTI = 20
@@ -99,10 +100,10 @@ def _parse_rank(path):
 
 
 def run_reference(pos, box, nside, mass, maxleaf=8, theta=0.4, split=-1.0, soft=-1.0, nranks=1, capture=0,
-                  repeat=1, workdir=None, timeout=3600, gpu=False, env_extra=None):
+                  repeat=1, workdir=None, timeout=3600, gpu=False, env_extra=None, open_newtonian=False):
     """Run one short-range force evaluation of the unmodified reference on `pos` (N x 3 float64, in
     [0, box)) at `nranks` ranks of the fork/socketpair mini-MPI.  Returns a list with one dict per rank."""
-    exe = REF_EXE_GPU if gpu else REF_EXE
+    exe = REF_EXE_GPU if gpu else (REF_EXE_OPEN if open_newtonian else REF_EXE)
     if not os.path.exists(exe):
         raise RuntimeError("oracle/_ref/ref_fmm is not built (run `make -C oracle ref` where /root/reference exists)")
     pos = np.ascontiguousarray(pos, dtype=np.float64)

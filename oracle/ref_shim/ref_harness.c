@@ -87,6 +87,8 @@ static void set_force_params(const PnRefParams *p) {
     if (p->split > 0.0) splitRadius = p->split;
     cutoffRadius = 4.5 * splitRadius;
     if (p->soft >= 0.0) SoftenScale = p->soft;
+    BoxMinimum = 0.0;            /* src/initial.c:495-497 (used by the non-periodic build, src/fmm.c:350-351) */
+    BoxMaximum = BOXSIZE;
 }
 
 int pn_ref_run(const double *pos, const PnRefParams *p, const char *outprefix) {

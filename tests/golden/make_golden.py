@@ -98,5 +98,27 @@ def main():
                 print("   LET captures on rank 0:", len(rc), "remote m2l pairs:", sum(len(c["m2l_s"]) for c in rc))
 
 
-if __name__ == "__main__":
+def merger():
+    """configs[1]: demo/ic_merger.gdt2 (60000 particles, BoxSize 0, positions in [-192, 192]) shifted by +200 into a
+    BOXSIZE 400 box, run through the reference built WITHOUT -DPERIODIC_CONDITION -DLONGSHORT (oracle/_ref/ref_fmm_open):
+    plain Newtonian P2P and G = 1/r M2L, no images.  All particles get MASSPART = head.mass[1] (src/snapshot.c:89)."""
+    pos32, hd = pn_ref.read_gadget2_positions("/root/reference/demo/ic_merger.gdt2")
+    np.save(os.path.join(HERE, "merger_pos_f32.npy"), pos32.astype(np.float32))
+    assert np.array_equal(pos32.astype(np.float32).astype(np.float64), pos32)
+    pos = pos32 + 200.0
+    mass, box = float(hd["mass"][1]), 400.0
+    for nranks in (1, 2):
+        r = pn_ref.run_reference(pos, box, 8, mass, maxleaf=8, theta=0.4, nranks=nranks, capture=1, open_newtonian=True, timeout=900)
+        acc = pn_ref.gather_acc(r, len(pos))
+        np.savez_compressed(os.path.join(HERE, f"merger_open_np{nranks}.npz"), acc=acc, box=box, mass=mass, nside=8, maxleaf=8, theta=0.4,
+                            shift=200.0, soft=r[0]["soft"], **counters(r))
+        print(f"merger open np={nranks}: rms|acc|={np.sqrt((acc**2).sum(1).mean()):.10e}", {k: v.tolist() for k, v in counters(r).items() if k.startswith(("idx", "walk", "p2p", "nint"))})
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "merger":
+    merger()
+
+
+if __name__ == "__main__" and len(sys.argv) == 1:
     main()
+    merger()

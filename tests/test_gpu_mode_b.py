@@ -159,3 +159,39 @@ def test_empty_and_tiny(pn2, oracle):
     ref_acc[tb.ids] = ref["acc"]
     assert rms_rel(acc, ref_acc) < 1e-4
     ctx.close()
+
+
+@pytest.mark.parametrize("nranks", [1, 2])
+def test_merger_ic_vs_reference(pn2, oracle, nranks):
+    """configs[1]: demo/ic_merger.gdt2 (clustered, non-periodic, Newtonian build): Mode B against the unmodified
+    reference's golden accelerations (3.7 M M2L pairs, 1.6e9 interactions), 1 rank and 2 ranks (in-process exchange)."""
+    import os
+    from conftest import GOLDEN
+    import domains
+    g = load_golden(f"merger_open_np{nranks}.npz")
+    pos = np.load(os.path.join(GOLDEN, "merger_pos_f32.npy")).astype(np.float64) + float(g["shift"])
+    box = float(g["box"])
+    prm_o = oracle.make_params(box, int(g["nside"]), len(pos), float(g["mass"]), maxleaf=8, theta=0.4, periodic=0, longshort=0)
+    for precision in (0, 1):
+        if nranks == 1:
+            ctx = make_ctx(pn2, prm_o, precision)
+            acc = ctx.force_step(pos)
+            infos = [ctx.step_info()]
+            ctx.close()
+        else:
+            doms = domains.domain_boxes(nranks, box)
+            owner = domains.domain_of(pos, nranks, box)
+            idx = [np.nonzero(owner == r)[0] for r in range(nranks)]
+            ctxs = [make_ctx(pn2, prm_o, precision) for _ in range(nranks)]
+            accs = pn2.force_step_local_ranks(ctxs, [pos[i] for i in idx], doms)
+            acc = np.zeros_like(pos)
+            for r in range(nranks):
+                acc[idx[r]] = accs[r]
+            infos = [c.step_info() for c in ctxs]
+            for c in ctxs:
+                c.close()
+        err = rms_rel(acc, g["acc"])
+        print(f"merger IC NP={nranks} precision {precision}: rms rel err vs reference golden {err:.3e}; M2L pairs {sum(i['n_m2l_pairs'] for i in infos)}")
+        assert sum(i["n_interactions"] for i in infos) == int(g["nint_local"].sum() + g["p2p_count_remote"].sum())
+        assert sum(i["n_m2l_pairs"] for i in infos) == int(g["walk_m2l_count"].sum())
+        assert err < TOL[precision] and err < (1e-10 if precision == 0 else 3e-5)

@@ -156,3 +156,40 @@ def test_operator_identities(oracle):
     s = s1 + s2
     L.pno_l2l(s[0], s[1], s[2], dp(Lc), dp(Ld))
     np.testing.assert_allclose(Lb, Ld, rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.parametrize("nranks", [1, 2])
+def test_merger_open_newtonian(oracle, nranks):
+    """configs[1]: demo/ic_merger.gdt2 through the reference built without -DPERIODIC_CONDITION -DLONGSHORT
+    (plain 1/r^2 P2P, G = 1/r M2L, no images): pins the oracle's non-periodic / Newtonian branches."""
+    import os
+    from conftest import GOLDEN
+    g = load_golden(f"merger_open_np{nranks}.npz")
+    pos = np.load(os.path.join(GOLDEN, "merger_pos_f32.npy")).astype(np.float64) + float(g["shift"])
+    prm = oracle.make_params(float(g["box"]), int(g["nside"]), len(pos), float(g["mass"]), maxleaf=8, theta=0.4, periodic=0, longshort=0)
+    assert prm.soft == float(g["soft"])
+    acc, cnt = oracle.force(pos, prm, nranks)
+    assert cnt["p2p_pairs"] == int(g["idxP2P"].sum()) and cnt["m2l_pairs"] == int(g["idxM2L"].sum())
+    assert cnt["int_local"] == int(g["nint_local"].sum()) and cnt["int_remote"] == int(g["p2p_count_remote"].sum())
+    assert cnt["m2l_calls"] == int(g["walk_m2l_count"].sum())
+    assert rms_rel(acc, g["acc"]) < 1e-12
+
+
+def test_device_tree_restatement_has_the_reference_leaf_sets(oracle, demo_pos):
+    """The Mode B tree (integer-mean, level-synchronous: oracle.TreeB restates the DEVICE builder) partitions the
+    demo IC and the merger IC into the same leaf particle sets as the reference's build_kdtree."""
+    import os
+    from conftest import GOLDEN
+    merger = np.load(os.path.join(GOLDEN, "merger_pos_f32.npy")).astype(np.float64) + 200.0
+    for pos, box in ((demo_pos, 100000.0), (merger, 400.0)):
+        ta = oracle.Tree(pos, 8, [0, 0, 0], [box] * 3)
+        tb = oracle.TreeB(pos, 8, [0, 0, 0], [box] * 3)
+        la, lb = ta.leaves(), tb.leaves()
+        sa = set(tuple(sorted(ta.ids[i:i + n])) for i, n in zip(la["ipart"], la["npart"]))
+        sb = set(tuple(sorted(tb.ids[i:i + n])) for i, n in zip(lb["ipart"], lb["npart"]))
+        assert sa == sb
+        # every particle lies inside its leaf's box
+        c, w = lb["center"], lb["width"]
+        k = np.repeat(np.arange(tb.nleaf), lb["npart"])
+        order = np.concatenate([np.arange(i, i + n) for i, n in zip(lb["ipart"], lb["npart"])])
+        assert (np.abs(tb.pos[order] - c[k]) <= 0.5 * w[k] + 1e-9).all()
