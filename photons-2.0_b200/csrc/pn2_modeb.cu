@@ -103,8 +103,12 @@ extern "C" int pn2_step_finish(pn2_ctx *h, double *d_acc) {
         if (cnt[3] & 1) { pn2_set_error("pn2: walk stack overflow (pathological particle distribution)"); return PN2_ERR_NOMEM; }
         bool redo = false;
         if (cnt[3] & 2) {                                              // span buffer too small
+            // a pass that ran out of room truncates the deeper levels' lists, so cnt[6] can underestimate the need:
+            // grow at least geometrically so that the retries converge
             unsigned long long want = cnt[6] + cnt[6] / 4 + 1024;
-            if (want >= (1ULL << 32)) { pn2_set_error("pn2: frontier lists exceed 64 GB"); return PN2_ERR_NOMEM; }
+            if (want < 2 * h->span_cap16) want = 2 * h->span_cap16;
+            if (want >= (1ULL << 32)) want = (1ULL << 32) - 1;
+            if (want <= h->span_cap16) { pn2_set_error("pn2: frontier lists exceed 64 GB"); return PN2_ERR_NOMEM; }
             h->span_cap16 = want;
             h->spans.release();
             PN2_TRY(h->spans.ensure(4 * (size_t)h->span_cap16));
@@ -113,13 +117,14 @@ extern "C" int pn2_step_finish(pn2_ctx *h, double *d_acc) {
         }
         if (cnt[1] > h->m2l_cap) {                                     // M2L pair buffer too small
             size_t cap = (size_t)cnt[1] + (size_t)cnt[1] / 4 + 1024;
+            if (redo && cap < 2 * h->m2l_cap) cap = 2 * h->m2l_cap;   // counted on truncated lists: may still be short
             h->m2l_pairs.release();
             PN2_TRY(h->m2l_pairs.ensure(2 * cap));
             h->m2l_cap = cap;
             redo = true;
         }
         if (!redo) break;
-        if (attempt >= 3) { pn2_set_error("pn2: interaction lists do not fit"); return PN2_ERR_NOMEM; }
+        if (attempt >= 8) { pn2_set_error("pn2: interaction lists do not fit"); return PN2_ERR_NOMEM; }
         CUDA_TRY(cudaMemsetAsync(h->acc.p, 0, 3 * (size_t)n * sizeof(double), st));
     }
     h->span_used16 = cnt[6];

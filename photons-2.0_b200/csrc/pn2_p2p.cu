@@ -24,9 +24,6 @@ p2p_csr_f32_kernel(long nseg, const int *__restrict__ seg_sink, const long *__re
     if (seg >= nseg) return;
     const int q = lane / SW, j = lane % SW;
 
-    float qc[PN2_RDEG + 1];
-#pragma unroll
-    for (int k = 0; k <= PN2_RDEG; k++) qc[k] = pc.q[k];
     const float inv_eps = pc.inv_eps;
 
     const int sink = seg_sink[seg];
@@ -37,6 +34,11 @@ p2p_csr_f32_kernel(long nseg, const int *__restrict__ seg_sink, const long *__re
         xi = p.x; yi = p.y; zi = p.z;
     }
     float ax = 0.f, ay = 0.f, az = 0.f;
+#if PN2_PACKED
+    P2PSinkPk sk;
+    sk.nx = pk2(-xi, -xi); sk.ny = pk2(-yi, -yi); sk.nz = pk2(-zi, -zi);
+    sk.ax = sk.ay = sk.az = pk2(0.f, 0.f);
+#endif
     const long o0 = seg_off[seg], o1 = seg_off[seg + 1];
     unsigned long long nint = 0;
 
@@ -64,14 +66,25 @@ p2p_csr_f32_kernel(long nseg, const int *__restrict__ seg_sink, const long *__re
     int buf = 0;
     float4 pnext = load_stage(o0);
     for (long base = o0; base < o1; base += NSL) {
+#if PN2_PACKED
+        float *stg = reinterpret_cast<float *>(sm[wib][buf]);
+        pk_store<SW, LONGSHORT>(stg, q, j, pnext.x, pnext.y, pnext.z, pnext.w);
+        __syncwarp();
+        if (base + NSL < o1) pnext = load_stage(base + NSL);   // in flight during the compute below
+        pk_row<SW, LONGSHORT>(stg, q, sk, inv_eps);
+#else
         sm[wib][buf][q * ST::ROW + j] = pnext;
         __syncwarp();
         if (base + NSL < o1) pnext = load_stage(base + NSL);   // in flight during the compute below
         const float4 *row = &sm[wib][buf][q * ST::ROW];
 #pragma unroll
-        for (int k = 0; k < SW; k++) p2p_interact_f32<LONGSHORT>(row[k], xi, yi, zi, ax, ay, az, qc, inv_eps);
+        for (int k = 0; k < SW; k++) p2p_interact_f32<LONGSHORT>(row[k], xi, yi, zi, ax, ay, az, inv_eps);
+#endif
         buf ^= 1;
     }
+#if PN2_PACKED
+    { float lo, hi; unpk2(sk.ax, lo, hi); ax = lo + hi; unpk2(sk.ay, lo, hi); ay = lo + hi; unpk2(sk.az, lo, hi); az = lo + hi; }
+#endif
     // reduce the slices
 #pragma unroll
     for (int m = SW; m < 32; m <<= 1) {

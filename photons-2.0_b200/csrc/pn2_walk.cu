@@ -39,6 +39,8 @@ struct WalkArgs {
     const LeafDesc *desc;
     const int *parent;
     const float4 *rel;
+    const float *tiles;                // FP32 mode: leaf tiles (see walk_fused_kernel), pad_tile = the all-padding tile
+    int pad_tile;
     const double *pos;
     double *acc;
     double cutoff, theta;
@@ -277,23 +279,51 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NODE_MIN_BLOCKS) frontier_nod
 // ------------------------------------------------------------------------------------------------
 // Pass 2: one warp per sink LEAF: F(leaf) = O(parent) -> source leaves -> P2P (and leaf-level M2L pairs)
 // ------------------------------------------------------------------------------------------------
-// A resolved source leaf in the per-warp queue: everything the stage loader needs, computed once by the
-// lane that found it (not by the 8 lanes that later load its particles)
-struct __align__(16) SrcEnt {
+// FP32 mode reads sources as LEAF TILES: every leaf owns one tile of SW slots in HBM, already in the packed-pair
+// layout of the P2P loop (pn2_p2p.cuh: SW/2 pairs of {x0 x1 y0 y1 | z0 z1 w0 w1}, leaf-centre-relative, units of
+// 2 rs, unused slots = far-away zero-weight padding).  Staging a source leaf is then a plain 16 * SW byte copy:
+// the warp issues cp.async (LDGSTS.128, no registers, no arithmetic) for a whole BATCH of queued leaves at once and
+// goes on walking while the copies land; the per-leaf centre offset is applied on the SINK side (3 FADD per
+// lane and stage) instead of to every staged particle.
+//
+// A resolved source leaf in the per-warp queue
+struct __align__(16) SrcEnt {   // FP64 / dump modes
     int first, npart;       // particle range
-    unsigned tag;           // cell | image << 26 (dump mode, FP64 mode)
+    unsigned tag;           // cell | image << 26
+    int pad0;
+    float pad1, pad2, pad3, pad4;
+};
+struct __align__(16) TileEnt {  // FP32 mode
+    int tile;               // tile index (local leaf id, or nleaf + received-leaf ordinal)
     float dx, dy, dz;       // source leaf centre - sink leaf centre (+ image shift), units of 2 rs
-    float pad0, pad1;
 };
 
-template <int SW, int MODE>     // MODE 0: FP32 P2P, 1: FP64 P2P, 2: dump lists (no arithmetic)
+__device__ __forceinline__ void cp_async16(unsigned dst_shared, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst_shared), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int SW, int MODE>
+struct WalkSmem {
+    static constexpr int NSL = 32 / SW;
+    static constexpr int NST = 8;                         // stages per batch
+    static constexpr int BATCH = NST * NSL;               // queued source leaves per batch (32 / 16 / 8)
+    static constexpr int TB = 16 * SW;                    // tile bytes
+    static constexpr int ROWB = TB + 16;                  // row stride in shared memory: the 16 spare bytes hold the
+                                                          // leaf's {tile, dx, dy, dz} and de-conflict the NSL broadcast rows
+    static constexpr int STAGE_BYTES = MODE == 0 ? BATCH * ROWB : 16;
+    static constexpr int QENT = MODE == 0 ? (int)sizeof(TileEnt) : (int)sizeof(SrcEnt);
+};
+
+template <int SW, int MODE, bool LS>     // MODE 0: FP32 P2P (LS: with the long/short split factor), 1: FP64 P2P, 2: dump lists
 __global__ void __launch_bounds__(WALK_WARPS * 32, LEAF_MIN_BLOCKS)
 walk_fused_kernel(WalkArgs a, P2PConst pc) {
-    using ST = P2PStageF32<SW>;
-    constexpr int NSL = 32 / SW;
+    using WS = WalkSmem<SW, MODE>;
+    constexpr int NSL = WS::NSL, NST = WS::NST, BATCH = WS::BATCH, TB = WS::TB, ROWB = WS::ROWB;
     __shared__ unsigned s_stack[WALK_WARPS][STACK_CAP];
-    __shared__ SrcEnt s_srcq[WALK_WARPS][SRCQ_CAP];
-    __shared__ float4 s_stage[WALK_WARPS][2][ST::STAGE_F4];
+    __shared__ __align__(16) unsigned char s_srcq[WALK_WARPS][SRCQ_CAP * WS::QENT];
+    __shared__ __align__(16) unsigned char s_stage[WALK_WARPS][WS::STAGE_BYTES];
     __shared__ double s_sink[WALK_WARPS][6];
 
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -301,64 +331,65 @@ walk_fused_kernel(WalkArgs a, P2PConst pc) {
     if (leaf >= a.nleaf) return;
     const unsigned lt_mask = (1u << lane) - 1u;
     unsigned *stack = s_stack[wib];
-    SrcEnt *srcq = s_srcq[wib];
+    SrcEnt *srcq = reinterpret_cast<SrcEnt *>(s_srcq[wib]);
+    TileEnt *tileq = reinterpret_cast<TileEnt *>(s_srcq[wib]);
     const double *sink_g = s_sink[wib];
 
     // ---- sink leaf ----
     const int q = lane / SW, j = lane % SW;
     const LeafDesc sd = a.desc[leaf];
     if (lane < 6) s_sink[wib][lane] = a.geom[6 * (size_t)leaf + lane];
-    float xi = 0.f, yi = 0.f, zi = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
+    float xi = 0.f, yi = 0.f, zi = 0.f;
     double xd = 0, yd = 0, zd = 0, axd = 0, ayd = 0, azd = 0;
-    if (MODE == 0 && j < sd.npart) { float4 p = a.rel[sd.first + j]; xi = p.x; yi = p.y; zi = p.z; }
+    if (MODE == 0) {                 // slot j of the sink's own tile (padding slots compute, but are never written)
+        const float *t = a.tiles + (size_t)leaf * (4 * SW) + (j >> 1) * 8 + (j & 1);
+        xi = t[0]; yi = t[2]; zi = t[4];
+    }
     if (MODE == 1 && j < sd.npart) { const double *p = a.pos + 3 * (size_t)(sd.first + j); xd = p[0]; yd = p[1]; zd = p[2]; }
-    float qc[PN2_RDEG + 1];
-#pragma unroll
-    for (int k = 0; k <= PN2_RDEG; k++) qc[k] = pc.q[k];
+    P2PSinkPk sk;
+    sk.nx = sk.ny = sk.nz = sk.ax = sk.ay = sk.az = pk2(0.f, 0.f);
     const float inv_eps = pc.inv_eps;
     unsigned nsrc = 0, visits = 0, npairs = 0;
     long dump_pos = (MODE == 2 && a.pass == 1) ? a.lst_off[leaf] : 0;
     __syncwarp();
 
-    // ---- drain entries of the source queue through the staged P2P pipeline ----
-    int qhead = 0, qtail = 0, buf = 0;
-    // stage loader, split in two so that the global load stays in flight during the previous stage's arithmetic:
-    // issue() starts the LDG of this lane's source particle and keeps the leaf's centre offset; finish() adds the
-    // offset when the value is finally stored to shared memory.
-    float4 ld_r = make_float4(0.f, 0.f, 0.f, 0.f);
-    float ld_dx = 0.f, ld_dy = 0.f, ld_dz = 0.f;
-    auto issue = [&](int pos_, int limit) {
-        ld_r = make_float4(PN2_PAD_COORD, PN2_PAD_COORD, PN2_PAD_COORD, 0.f);
-        ld_dx = ld_dy = ld_dz = 0.f;
-        int idx = pos_ + q;
-        if (idx < limit) {
-            const SrcEnt *e = &srcq[idx & (SRCQ_CAP - 1)];
-            const int4 h4 = *reinterpret_cast<const int4 *>(e);           // first, npart, tag, dx
-            if (j < h4.y) {
-                const float2 d2 = *reinterpret_cast<const float2 *>(&e->dy);
-                ld_r = a.rel[h4.x + j];
-                ld_dx = __int_as_float(h4.w); ld_dy = d2.x; ld_dz = d2.y;
+    int qhead = 0, qtail = 0, inflight = 0;
+    // ---- FP32: batches of BATCH queued leaves through the tile pipeline ----
+    unsigned char *stage = s_stage[wib];
+    const unsigned stage_dst = (unsigned)__cvta_generic_to_shared(stage) + q * ROWB + j * 16;   // this lane's 16-byte chunk of row q
+    const char *tile_src = reinterpret_cast<const char *>(a.tiles) + j * 16;
+    auto issue_batch = [&](int cnt) {      // cnt <= BATCH queue entries from qhead, a multiple of NSL
+#pragma unroll
+        for (int s = 0; s < NST; s++) {
+            if (s * NSL < cnt) {
+                const int4 e = *reinterpret_cast<const int4 *>(&tileq[(qhead + s * NSL + q) & (SRCQ_CAP - 1)]);
+                cp_async16(stage_dst + s * NSL * ROWB, tile_src + (size_t)e.x * TB);
+                if (j == 0) *reinterpret_cast<int4 *>(stage + (s * NSL + q) * ROWB + TB) = e;
             }
         }
+        cp_async_commit();
+        inflight = cnt;
+        qhead += cnt;
     };
-    auto drain = [&](int limit) {          // consumes [qhead, limit)
-        if (MODE == 0) {
-            issue(qhead, limit);
-            for (int base = qhead; base < limit; base += NSL) {
-                s_stage[wib][buf][q * ST::ROW + j] = make_float4(ld_r.x + ld_dx, ld_r.y + ld_dy, ld_r.z + ld_dz, ld_r.w);
-                __syncwarp();
-                if (base + NSL < limit) issue(base + NSL, limit);
-                const float4 *row = &s_stage[wib][buf][q * ST::ROW];
-                if (pc.longshort) {
+    auto compute_batch = [&]() {
+        cp_async_wait_all();
+        __syncwarp();
 #pragma unroll
-                    for (int k = 0; k < SW; k++) p2p_interact_f32<true>(row[k], xi, yi, zi, ax, ay, az, qc, inv_eps);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < SW; k++) p2p_interact_f32<false>(row[k], xi, yi, zi, ax, ay, az, qc, inv_eps);
-                }
-                buf ^= 1;
+        for (int s = 0; s < NST; s++) {
+            if (s * NSL < inflight) {
+                const float *row = reinterpret_cast<const float *>(stage + (s * NSL + q) * ROWB);
+                const float4 o = *reinterpret_cast<const float4 *>(row + TB / 4);
+                const float nx = o.y - xi, ny = o.z - yi, nz = o.w - zi;          // x_j + (centre offset - x_i)
+                sk.nx = pk2(nx, nx); sk.ny = pk2(ny, ny); sk.nz = pk2(nz, nz);
+                pk_row<SW, LS>(row, 0, sk, inv_eps);
             }
-        } else if (MODE == 1) {
+        }
+        inflight = 0;
+        __syncwarp();                      // the stage is free for the next batch
+    };
+    // ---- FP64 / dump: consume [qhead, limit) directly ----
+    auto drain = [&](int limit) {
+        if (MODE == 1) {
             for (int idx = qhead + q; idx < limit; idx += NSL) {
                 const SrcEnt e = srcq[idx & (SRCQ_CAP - 1)];
                 const unsigned img = e.tag >> PN2_IMG_SHIFT;
@@ -374,7 +405,6 @@ walk_fused_kernel(WalkArgs a, P2PConst pc) {
                 for (int idx = qhead + lane; idx < limit; idx += 32) a.lst_src[dump_pos + (idx - qhead)] = srcq[idx & (SRCQ_CAP - 1)].tag;
             dump_pos += limit - qhead;
         }
-        npairs += limit - qhead;
         qhead = limit;
         __syncwarp();
     };
@@ -384,22 +414,22 @@ walk_fused_kernel(WalkArgs a, P2PConst pc) {
     rd.init(a.spans, a.o_head[a.parent[leaf]]);
     int ssize = 0;
     int err = 0;
-    while (true) {
-        if (ssize < 32 && rd.more()) {
+    // one step of the walk: up to 32 entries of the stack; returns false when F(leaf) is exhausted
+    auto walk_step = [&]() -> bool {
+        while (ssize < 32 && rd.more()) {
             unsigned e = 0;
             int n = rd.fetch(lane, e);
             if (lane < n) stack[ssize + lane] = e;
             ssize += n;
             __syncwarp();
-            if (n > 0 && ssize < 32 && rd.more()) continue;
         }
-        if (ssize == 0) break;
+        if (ssize == 0) return false;
         int k = ssize < 32 ? ssize : 32;
         if (ssize > STACK_CAP - 64) k = 1;
         const int sbase = ssize - k;
         int npush = 0, emit_p = 0, emit_m = 0;
         unsigned p0 = 0, p1 = 0, jme = 0;
-        SrcEnt ent;
+        int4 ent = make_int4(0, 0, 0, 0);
         if (lane < k) {
             jme = stack[sbase + lane];
             const int jm = (int)(jme & PN2_CELL_MASK);
@@ -408,11 +438,14 @@ walk_fused_kernel(WalkArgs a, P2PConst pc) {
                 // leaf x leaf: always a P2P pair (src/fmm.c:438-451, src/remotes.c:228-240)
                 emit_p = 1;
                 const LeafDesc d = a.desc[jm];
-                ent.first = d.first; ent.npart = d.npart; ent.tag = jme;
-                ent.dx = (float)(((d.c[0] + pc.shift[img][0]) - sd.c[0]) * pc.inv2rs);
-                ent.dy = (float)(((d.c[1] + pc.shift[img][1]) - sd.c[1]) * pc.inv2rs);
-                ent.dz = (float)(((d.c[2] + pc.shift[img][2]) - sd.c[2]) * pc.inv2rs);
-                ent.pad0 = 0.f; ent.pad1 = 0.f;
+                if (MODE == 0) {
+                    ent.x = jm < a.nleaf ? jm : jm - a.rleaf0 + a.nleaf;
+                    ent.y = __float_as_int((float)(((d.c[0] + pc.shift[img][0]) - sd.c[0]) * pc.inv2rs));
+                    ent.z = __float_as_int((float)(((d.c[1] + pc.shift[img][1]) - sd.c[1]) * pc.inv2rs));
+                    ent.w = __float_as_int((float)(((d.c[2] + pc.shift[img][2]) - sd.c[2]) * pc.inv2rs));
+                } else {
+                    ent = make_int4(d.first, d.npart, (int)jme, 0);
+                }
                 nsrc += (unsigned)(d.npart - ((jme == (unsigned)leaf) ? 1 : 0));
             } else {
                 double cj[3], wj[3];
@@ -436,25 +469,51 @@ walk_fused_kernel(WalkArgs a, P2PConst pc) {
         const unsigned m2 = __ballot_sync(0xffffffffu, npush == 2);
         int pos0 = sbase + 2 * __popc(m2 & lt_mask);
         const int newsize = sbase + 2 * __popc(m2);
-        if (newsize > STACK_CAP) { err = 1; break; }
+        if (newsize > STACK_CAP) { err = 1; return false; }
         if (npush == 2) { stack[pos0] = p0; stack[pos0 + 1] = p1; }
         ssize = newsize;
         const unsigned mp = __ballot_sync(0xffffffffu, emit_p);
         if (emit_p) {
-            SrcEnt *dst = &srcq[(qtail + __popc(mp & lt_mask)) & (SRCQ_CAP - 1)];
-            *reinterpret_cast<int4 *>(dst) = make_int4(ent.first, ent.npart, (int)ent.tag, __float_as_int(ent.dx));
-            *reinterpret_cast<float4 *>(&dst->dy) = make_float4(ent.dy, ent.dz, 0.f, 0.f);
+            const int at = (qtail + __popc(mp & lt_mask)) & (SRCQ_CAP - 1);
+            if (MODE == 0) *reinterpret_cast<int4 *>(&tileq[at]) = ent;
+            else *reinterpret_cast<int4 *>(&srcq[at]) = ent;
         }
         qtail += __popc(mp);
+        npairs += __popc(mp);
         emit_m2l_pairs(a, lane, lt_mask, emit_m, (unsigned)leaf, jme);
         __syncwarp();
-        if (qtail - qhead >= 32) drain(qhead + ((qtail - qhead) / NSL) * NSL);
+        return true;
+    };
+    // walk until a batch of source leaves is queued, evaluate the batch whose tiles were requested one round
+    // earlier, request the tiles of the new batch, walk on
+    constexpr int QBATCH = MODE == 0 ? BATCH : 32;
+    bool walking = true;
+    while (true) {
+        while (walking && qtail - qhead < QBATCH) walking = walk_step();
+        if (MODE == 0 && inflight) compute_batch();
+        const int avail = qtail - qhead;
+        if (avail == 0 || err) break;                                // walking implies avail >= QBATCH
+        if (MODE == 0) {
+            int cnt = BATCH;
+            if (avail < BATCH) {                                       // the last batch: pad its last stage with the padding tile
+                cnt = ((avail + NSL - 1) / NSL) * NSL;
+                if (lane < cnt - avail) *reinterpret_cast<int4 *>(&tileq[(qtail + lane) & (SRCQ_CAP - 1)]) = make_int4(a.pad_tile, 0, 0, 0);
+                qtail = qhead + cnt;
+                __syncwarp();
+            }
+            issue_batch(cnt);
+        } else {
+            drain(walking ? qhead + (avail / NSL) * NSL : qtail);
+        }
     }
-    if (qtail > qhead) drain(qtail);
     if (err) { if (lane == 0) atomicOr(&a.counters[3], 1ULL); return; }
 
     // ---- results ----
     if (MODE == 0) {
+        float ax, ay, az, hi;
+        unpk2(sk.ax, ax, hi); ax += hi;
+        unpk2(sk.ay, ay, hi); ay += hi;
+        unpk2(sk.az, az, hi); az += hi;
 #pragma unroll
         for (int m = SW; m < 32; m <<= 1) {
             ax += __shfl_xor_sync(0xffffffffu, ax, m);
@@ -491,12 +550,30 @@ walk_fused_kernel(WalkArgs a, P2PConst pc) {
     }
 }
 
+// Leaf tiles (FP32 mode): slot j of tile t <- particle j of the leaf, packed-pair layout; tile nt = all padding.
+// Tiles 0..nleaf-1 are the local leaves, nleaf.. the received LET leaves (cells rleaf0..).
+template <int SW>
+__global__ void tile_kernel(int nt, int nleaf, int rleaf0, const LeafDesc *__restrict__ desc, const float4 *__restrict__ rel,
+                            float *__restrict__ tiles) {
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int tile = (int)(t / SW), j = (int)(t % SW);
+    if (tile > nt) return;
+    float4 p = make_float4(PN2_PAD_COORD, PN2_PAD_COORD, PN2_PAD_COORD, 0.f);
+    if (tile < nt) {
+        const LeafDesc d = desc[tile < nleaf ? tile : tile - nleaf + rleaf0];
+        if (j < d.npart) p = rel[d.first + j];
+    }
+    float *o = tiles + (size_t)tile * (4 * SW) + (j >> 1) * 8 + (j & 1);
+    o[0] = p.x; o[2] = p.y; o[4] = p.z; o[6] = p.w;
+}
+
 template <int SW>
 static void launch_mode(pn2_ctx *h, const WalkArgs &a, int mode) {
     unsigned grid = (unsigned)((a.nleaf + WALK_WARPS - 1) / WALK_WARPS);
-    if (mode == 0) walk_fused_kernel<SW, 0><<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
-    else if (mode == 1) walk_fused_kernel<SW, 1><<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
-    else walk_fused_kernel<SW, 2><<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
+    if (mode == 0 && h->prm.longshort) walk_fused_kernel<SW, 0, true><<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
+    else if (mode == 0) walk_fused_kernel<SW, 0, false><<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
+    else if (mode == 1) walk_fused_kernel<SW, 1, true><<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
+    else walk_fused_kernel<SW, 2, true><<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
     h->launches++;
 }
 
@@ -547,6 +624,19 @@ int pn2_walk_fused(pn2_ctx *h, int dump) {
     a.emit_m2l = dump == 0;
     int mode = dump ? 2 : (h->prm.precision == PN2_FP64 ? 1 : 0);
     int ml = h->prm.maxleaf;
+    if (mode == 0) {
+        // leaf tiles of the local and the received leaves (+ one padding tile)
+        const int sw = ml <= 8 ? 8 : (ml <= 16 ? 16 : 32);
+        const int nt = h->nleaf + h->nrl;
+        PN2_TRY(h->tiles.ensure(((size_t)nt + 1) * 4 * sw));
+        const long nthr = ((long)nt + 1) * sw;
+        const unsigned g = (unsigned)((nthr + 255) / 256);
+        if (sw == 8) tile_kernel<8><<<g, 256, 0, h->stream>>>(nt, h->nleaf, h->ncell, h->desc.p, h->rel.p, h->tiles.p);
+        else if (sw == 16) tile_kernel<16><<<g, 256, 0, h->stream>>>(nt, h->nleaf, h->ncell, h->desc.p, h->rel.p, h->tiles.p);
+        else tile_kernel<32><<<g, 256, 0, h->stream>>>(nt, h->nleaf, h->ncell, h->desc.p, h->rel.p, h->tiles.p);
+        h->launches++;
+        a.tiles = h->tiles.p; a.pad_tile = nt;
+    }
     if (ml <= 8) launch_mode<8>(h, a, mode);
     else if (ml <= 16) launch_mode<16>(h, a, mode);
     else launch_mode<32>(h, a, mode);
