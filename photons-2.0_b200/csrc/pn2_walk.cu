@@ -27,7 +27,7 @@
 #define SRCQ_CAP 64
 #define OBUF_CAP 256              // per-warp staging of O(im) before it is flushed to a span
 #ifndef LEAF_MIN_BLOCKS
-#define LEAF_MIN_BLOCKS 8          // register cap of the leaf kernel (64 regs, 32 warps/SM): best of 5..8 measured at 256^3
+#define LEAF_MIN_BLOCKS 5          // register cap of the leaf kernel (102 regs, 20 warps/SM): best of 4..8 measured at 256^3
 #endif
 
 struct WalkArgs {
@@ -277,255 +277,169 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NODE_MIN_BLOCKS) frontier_nod
 }
 
 // ------------------------------------------------------------------------------------------------
-// Pass 2: one warp per sink LEAF: F(leaf) = O(parent) -> source leaves -> P2P (and leaf-level M2L pairs)
+// Pass 2: F(leaf) = O(parent) -> source leaves -> P2P (and leaf-level M2L pairs)
 // ------------------------------------------------------------------------------------------------
-// FP32 mode reads sources as LEAF TILES: every leaf owns one tile of SW slots in HBM, already in the packed-pair
-// layout of the P2P loop (pn2_p2p.cuh: SW/2 pairs of {x0 x1 y0 y1 | z0 z1 w0 w1}, leaf-centre-relative, units of
-// 2 rs, unused slots = far-away zero-weight padding).  Staging a source leaf is then a plain 16 * SW byte copy:
-// the warp issues cp.async (LDGSTS.128, no registers, no arithmetic) for a whole BATCH of queued leaves at once and
-// goes on walking while the copies land; the per-leaf centre offset is applied on the SINK side (3 FADD per
-// lane and stage) instead of to every staged particle.
-//
-// A resolved source leaf in the per-warp queue
-struct __align__(16) SrcEnt {   // FP64 / dump modes
-    int first, npart;       // particle range
-    unsigned tag;           // cell | image << 26
-    int pad0;
-    float pad1, pad2, pad3, pad4;
-};
-struct __align__(16) TileEnt {  // FP32 mode
-    int tile;               // tile index (local leaf id, or nleaf + received-leaf ordinal)
-    float dx, dy, dz;       // source leaf centre - sink leaf centre (+ image shift), units of 2 rs
+// LeafWalk resolves the frontier of ONE sink leaf, 32 stack entries per step, and appends the source leaves it
+// finds to a per-warp queue of 16-byte entries:
+//     FP32 mode (MODE 0): {tile, dx, dy, dz}  tile = leaf tile index, d = source leaf centre - sink leaf centre
+//                                             (+ image shift) in units of 2 rs
+//     FP64 / dump modes : {first, npart, cell | image << 26, 0}
+template <int MODE, int U, int QCAP>     // U = stack entries per lane and step (32 U per step): the walk is latency-bound,
+struct LeafWalk {                        // wider steps mean fewer dependent round trips per leaf; QCAP = queue capacity
+    SpanReader rd;
+    unsigned *stack;
+    int4 *queue;
+    const double *sink_g;        // shared: centre, width of the sink leaf
+    LeafDesc sd;
+    int leaf, ssize, qtail, err;
+    unsigned nsrc, visits, npairs;
+    unsigned pre_e;              // the next chunk of F(leaf), requested one step ahead (its latency overlaps the step)
+    int pre_n;
+
+    __device__ __forceinline__ void begin(const WalkArgs &a, int leaf_, unsigned *stack_, int4 *queue_, double *sink_smem, int lane) {
+        leaf = leaf_; stack = stack_; queue = queue_; sink_g = sink_smem;
+        rd.init(a.spans, a.o_head[a.parent[leaf]]);
+        pre_e = 0;
+        pre_n = rd.fetch(lane, pre_e);
+        sd = a.desc[leaf];
+        if (lane < 6) sink_smem[lane] = a.geom[6 * (size_t)leaf + lane];
+        ssize = 0; qtail = 0; err = 0; nsrc = 0; visits = 0; npairs = 0;
+        __syncwarp();
+    }
+    // returns false when F(leaf) is exhausted (or the stack overflowed: err)
+    __device__ __forceinline__ bool step(const WalkArgs &a, const P2PConst &pc, int lane) {
+        const unsigned lt_mask = (1u << lane) - 1u;
+        while (ssize < 32 * U && pre_n > 0) {
+            if (lane < pre_n) stack[ssize + lane] = pre_e;
+            ssize += pre_n;
+            pre_n = rd.fetch(lane, pre_e);
+            __syncwarp();
+        }
+        if (ssize == 0) return false;
+        int k = ssize < 32 * U ? ssize : 32 * U;
+        if (k > STACK_CAP - ssize) k = STACK_CAP - ssize > 0 ? STACK_CAP - ssize : 1;     // every entry can grow the stack by one
+        const int sbase = ssize - k;
+        // ---- phase 1: every global load of the step is requested before any of them is used (one round trip):
+        //      a leaf's descriptor {centre, first, npart} or a node's geometry {centre, width} + sons
+        unsigned jme[U];
+        bool lj[U];
+        double2 r0[U], r1[U], r2[U];
+        int2 sons[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            jme[u] = 0; lj[u] = false;
+            r0[u] = r1[u] = r2[u] = make_double2(0.0, 0.0);
+            sons[u] = make_int2(0, 0);
+            if (u * 32 + lane < k) {
+                jme[u] = stack[sbase + u * 32 + lane];
+                const int jm = (int)(jme[u] & PN2_CELL_MASK);
+                lj[u] = jm < a.nleaf || (jm >= a.rleaf0 && jm < a.rnode0);
+                const double2 *rec = lj[u] ? reinterpret_cast<const double2 *>(a.desc + jm) : reinterpret_cast<const double2 *>(a.geom + 6 * (size_t)jm);
+                r0[u] = rec[0]; r1[u] = rec[1];
+                if (!lj[u]) { r2[u] = rec[2]; sons[u] = *reinterpret_cast<const int2 *>(a.son + 2 * (size_t)jm); }
+            }
+        }
+        visits += k;
+        __syncwarp();                      // the popped entries are in registers: the stack may be overwritten from sbase
+        // ---- phase 2: decide, then compact pushes / queue entries / M2L pairs with ballots ----
+        int top = sbase;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            int npush = 0, emit_p = 0, emit_m = 0;
+            unsigned p0 = 0, p1 = 0;
+            int4 ent = make_int4(0, 0, 0, 0);
+            if (u * 32 + lane < k) {
+                const int jm = (int)(jme[u] & PN2_CELL_MASK);
+                const unsigned img = jme[u] >> PN2_IMG_SHIFT, imgbits = jme[u] & ~PN2_CELL_MASK;
+                if (lj[u]) {
+                    // leaf x leaf: always a P2P pair (src/fmm.c:438-451, src/remotes.c:228-240)
+                    emit_p = 1;
+                    const int dfirst = __double2loint(r1[u].y), dnpart = __double2hiint(r1[u].y);
+                    if (MODE == 0) {
+                        ent.x = jm < a.nleaf ? jm : jm - a.rleaf0 + a.nleaf;
+                        ent.y = __float_as_int((float)(((r0[u].x + pc.shift[img][0]) - sd.c[0]) * pc.inv2rs));
+                        ent.z = __float_as_int((float)(((r0[u].y + pc.shift[img][1]) - sd.c[1]) * pc.inv2rs));
+                        ent.w = __float_as_int((float)(((r1[u].x + pc.shift[img][2]) - sd.c[2]) * pc.inv2rs));
+                    } else {
+                        ent = make_int4(dfirst, dnpart, (int)jme[u], 0);
+                    }
+                    nsrc += (unsigned)(dnpart - ((jme[u] == (unsigned)leaf) ? 1 : 0));
+                } else {
+                    double cj[3] = {r0[u].x, r0[u].y, r1[u].x}, wj[3] = {r1[u].y, r2[u].x, r2[u].y};
+                    int pruned = 0;
+                    if (img != 0 || jm >= a.rleaf0) {
+                        pruned = pruned_dev(cj, wj, pc.shift[img], a.tc, a.tw, a.cutoff, a.theta, a.longshort);
+                        cj[0] += pc.shift[img][0]; cj[1] += pc.shift[img][1]; cj[2] += pc.shift[img][2];
+                    }
+                    int f = accept_dev(sink_g + 3, wj, sink_g[0] - cj[0], sink_g[1] - cj[1], sink_g[2] - cj[2], a.cutoff, a.theta,
+                                       a.longshort);
+                    if (f == 1 || (f == 0 && pruned)) emit_m = 1;        // forced M2L on a pruned node: src/remotes.c:442
+                    else if (f == 0) {
+                        npush = 2;
+                        p0 = (unsigned)sons[u].x | imgbits; p1 = (unsigned)sons[u].y | imgbits;
+                    }
+                }
+            }
+            const unsigned m2 = __ballot_sync(0xffffffffu, npush == 2);
+            const int pos0 = top + 2 * __popc(m2 & lt_mask);
+            top += 2 * __popc(m2);
+            if (top > STACK_CAP) { err = 1; return false; }
+            if (npush == 2) { stack[pos0] = p0; stack[pos0 + 1] = p1; }
+            const unsigned mp = __ballot_sync(0xffffffffu, emit_p);
+            if (emit_p) queue[(qtail + __popc(mp & lt_mask)) & (QCAP - 1)] = ent;
+            qtail += __popc(mp);
+            npairs += __popc(mp);
+            emit_m2l_pairs(a, lane, lt_mask, emit_m, (unsigned)leaf, jme[u]);
+        }
+        ssize = top;
+        __syncwarp();
+        return true;
+    }
 };
 
-__device__ __forceinline__ void cp_async16(unsigned dst_shared, const void *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst_shared), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-template <int SW, int MODE>
-struct WalkSmem {
-    static constexpr int NSL = 32 / SW;
-    static constexpr int NST = 8;                         // stages per batch
-    static constexpr int BATCH = NST * NSL;               // queued source leaves per batch (32 / 16 / 8)
-    static constexpr int TB = 16 * SW;                    // tile bytes
-    static constexpr int ROWB = TB + 16;                  // row stride in shared memory: the 16 spare bytes hold the
-                                                          // leaf's {tile, dx, dy, dz} and de-conflict the NSL broadcast rows
-    static constexpr int STAGE_BYTES = MODE == 0 ? BATCH * ROWB : 16;
-    static constexpr int QENT = MODE == 0 ? (int)sizeof(TileEnt) : (int)sizeof(SrcEnt);
-};
-
-template <int SW, int MODE, bool LS>     // MODE 0: FP32 P2P (LS: with the long/short split factor), 1: FP64 P2P, 2: dump lists
-__global__ void __launch_bounds__(WALK_WARPS * 32, LEAF_MIN_BLOCKS)
-walk_fused_kernel(WalkArgs a, P2PConst pc) {
-    using WS = WalkSmem<SW, MODE>;
-    constexpr int NSL = WS::NSL, NST = WS::NST, BATCH = WS::BATCH, TB = WS::TB, ROWB = WS::ROWB;
+// ---- FP64 parity mode and list dump: one warp per sink leaf, sources read through L1/L2 ----
+template <int SW, int MODE>     // MODE 1: FP64 P2P, 2: dump lists (no arithmetic)
+__global__ void __launch_bounds__(WALK_WARPS * 32) walk_leaf_kernel(WalkArgs a, P2PConst pc) {
+    constexpr int NSL = 32 / SW;
     __shared__ unsigned s_stack[WALK_WARPS][STACK_CAP];
-    __shared__ __align__(16) unsigned char s_srcq[WALK_WARPS][SRCQ_CAP * WS::QENT];
-    __shared__ __align__(16) unsigned char s_stage[WALK_WARPS][WS::STAGE_BYTES];
+    __shared__ int4 s_srcq[WALK_WARPS][SRCQ_CAP];
     __shared__ double s_sink[WALK_WARPS][6];
-
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int leaf = blockIdx.x * WALK_WARPS + wib;
     if (leaf >= a.nleaf) return;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    unsigned *stack = s_stack[wib];
-    SrcEnt *srcq = reinterpret_cast<SrcEnt *>(s_srcq[wib]);
-    TileEnt *tileq = reinterpret_cast<TileEnt *>(s_srcq[wib]);
-    const double *sink_g = s_sink[wib];
-
-    // ---- sink leaf ----
     const int q = lane / SW, j = lane % SW;
-    const LeafDesc sd = a.desc[leaf];
-    if (lane < 6) s_sink[wib][lane] = a.geom[6 * (size_t)leaf + lane];
-    float xi = 0.f, yi = 0.f, zi = 0.f;
+    LeafWalk<MODE, 1, SRCQ_CAP> w;
+    w.begin(a, leaf, s_stack[wib], s_srcq[wib], s_sink[wib], lane);
+    const LeafDesc sd = w.sd;
     double xd = 0, yd = 0, zd = 0, axd = 0, ayd = 0, azd = 0;
-    if (MODE == 0) {                 // slot j of the sink's own tile (padding slots compute, but are never written)
-        const float *t = a.tiles + (size_t)leaf * (4 * SW) + (j >> 1) * 8 + (j & 1);
-        xi = t[0]; yi = t[2]; zi = t[4];
-    }
     if (MODE == 1 && j < sd.npart) { const double *p = a.pos + 3 * (size_t)(sd.first + j); xd = p[0]; yd = p[1]; zd = p[2]; }
-    P2PSinkPk sk;
-    sk.nx = sk.ny = sk.nz = sk.ax = sk.ay = sk.az = pk2(0.f, 0.f);
-    const float inv_eps = pc.inv_eps;
-    unsigned nsrc = 0, visits = 0, npairs = 0;
     long dump_pos = (MODE == 2 && a.pass == 1) ? a.lst_off[leaf] : 0;
-    __syncwarp();
-
-    int qhead = 0, qtail = 0, inflight = 0;
-    // ---- FP32: batches of BATCH queued leaves through the tile pipeline ----
-    unsigned char *stage = s_stage[wib];
-    const unsigned stage_dst = (unsigned)__cvta_generic_to_shared(stage) + q * ROWB + j * 16;   // this lane's 16-byte chunk of row q
-    const char *tile_src = reinterpret_cast<const char *>(a.tiles) + j * 16;
-    auto issue_batch = [&](int cnt) {      // cnt <= BATCH queue entries from qhead, a multiple of NSL
-#pragma unroll
-        for (int s = 0; s < NST; s++) {
-            if (s * NSL < cnt) {
-                const int4 e = *reinterpret_cast<const int4 *>(&tileq[(qhead + s * NSL + q) & (SRCQ_CAP - 1)]);
-                cp_async16(stage_dst + s * NSL * ROWB, tile_src + (size_t)e.x * TB);
-                if (j == 0) *reinterpret_cast<int4 *>(stage + (s * NSL + q) * ROWB + TB) = e;
-            }
-        }
-        cp_async_commit();
-        inflight = cnt;
-        qhead += cnt;
-    };
-    auto compute_batch = [&]() {
-        cp_async_wait_all();
-        __syncwarp();
-#pragma unroll
-        for (int s = 0; s < NST; s++) {
-            if (s * NSL < inflight) {
-                const float *row = reinterpret_cast<const float *>(stage + (s * NSL + q) * ROWB);
-                const float4 o = *reinterpret_cast<const float4 *>(row + TB / 4);
-                const float nx = o.y - xi, ny = o.z - yi, nz = o.w - zi;          // x_j + (centre offset - x_i)
-                sk.nx = pk2(nx, nx); sk.ny = pk2(ny, ny); sk.nz = pk2(nz, nz);
-                pk_row<SW, LS>(row, 0, sk, inv_eps);
-            }
-        }
-        inflight = 0;
-        __syncwarp();                      // the stage is free for the next batch
-    };
-    // ---- FP64 / dump: consume [qhead, limit) directly ----
-    auto drain = [&](int limit) {
+    int qhead = 0;
+    auto drain = [&](int limit) {          // consumes [qhead, limit)
         if (MODE == 1) {
             for (int idx = qhead + q; idx < limit; idx += NSL) {
-                const SrcEnt e = srcq[idx & (SRCQ_CAP - 1)];
-                const unsigned img = e.tag >> PN2_IMG_SHIFT;
+                const int4 e = w.queue[idx & (SRCQ_CAP - 1)];
+                const unsigned img = (unsigned)e.z >> PN2_IMG_SHIFT;
                 const double sx = pc.shift[img][0], sy = pc.shift[img][1], sz = pc.shift[img][2];
-                for (int k = 0; k < e.npart; k++) {
-                    const double *p = a.pos + 3 * (size_t)(e.first + k);
+                for (int k = 0; k < e.y; k++) {
+                    const double *p = a.pos + 3 * (size_t)(e.x + k);
                     p2p_interact_f64(p[0] + sx, p[1] + sy, p[2] + sz, pc.mass, xd, yd, zd, axd, ayd, azd, pc.soft,
                                      pc.inv2rs, pc.longshort);
                 }
             }
         } else {
             if (a.pass == 1)
-                for (int idx = qhead + lane; idx < limit; idx += 32) a.lst_src[dump_pos + (idx - qhead)] = srcq[idx & (SRCQ_CAP - 1)].tag;
+                for (int idx = qhead + lane; idx < limit; idx += 32) a.lst_src[dump_pos + (idx - qhead)] = (unsigned)w.queue[idx & (SRCQ_CAP - 1)].z;
             dump_pos += limit - qhead;
         }
         qhead = limit;
         __syncwarp();
     };
-
-    // ---- resolve F(leaf) ----
-    SpanReader rd;
-    rd.init(a.spans, a.o_head[a.parent[leaf]]);
-    int ssize = 0;
-    int err = 0;
-    // one step of the walk: up to 32 entries of the stack; returns false when F(leaf) is exhausted
-    auto walk_step = [&]() -> bool {
-        while (ssize < 32 && rd.more()) {
-            unsigned e = 0;
-            int n = rd.fetch(lane, e);
-            if (lane < n) stack[ssize + lane] = e;
-            ssize += n;
-            __syncwarp();
-        }
-        if (ssize == 0) return false;
-        int k = ssize < 32 ? ssize : 32;
-        if (ssize > STACK_CAP - 64) k = 1;
-        const int sbase = ssize - k;
-        int npush = 0, emit_p = 0, emit_m = 0;
-        unsigned p0 = 0, p1 = 0, jme = 0;
-        int4 ent = make_int4(0, 0, 0, 0);
-        if (lane < k) {
-            jme = stack[sbase + lane];
-            const int jm = (int)(jme & PN2_CELL_MASK);
-            const unsigned img = jme >> PN2_IMG_SHIFT, imgbits = jme & ~PN2_CELL_MASK;
-            if (jm < a.nleaf || (jm >= a.rleaf0 && jm < a.rnode0)) {
-                // leaf x leaf: always a P2P pair (src/fmm.c:438-451, src/remotes.c:228-240)
-                emit_p = 1;
-                const LeafDesc d = a.desc[jm];
-                if (MODE == 0) {
-                    ent.x = jm < a.nleaf ? jm : jm - a.rleaf0 + a.nleaf;
-                    ent.y = __float_as_int((float)(((d.c[0] + pc.shift[img][0]) - sd.c[0]) * pc.inv2rs));
-                    ent.z = __float_as_int((float)(((d.c[1] + pc.shift[img][1]) - sd.c[1]) * pc.inv2rs));
-                    ent.w = __float_as_int((float)(((d.c[2] + pc.shift[img][2]) - sd.c[2]) * pc.inv2rs));
-                } else {
-                    ent = make_int4(d.first, d.npart, (int)jme, 0);
-                }
-                nsrc += (unsigned)(d.npart - ((jme == (unsigned)leaf) ? 1 : 0));
-            } else {
-                double cj[3], wj[3];
-                load_geom(a.geom, jm, cj, wj);
-                int pruned = 0;
-                if (img != 0 || jm >= a.rleaf0) {
-                    pruned = pruned_dev(cj, wj, pc.shift[img], a.tc, a.tw, a.cutoff, a.theta, a.longshort);
-                    cj[0] += pc.shift[img][0]; cj[1] += pc.shift[img][1]; cj[2] += pc.shift[img][2];
-                }
-                int f = accept_dev(sink_g + 3, wj, sink_g[0] - cj[0], sink_g[1] - cj[1], sink_g[2] - cj[2], a.cutoff, a.theta,
-                                   a.longshort);
-                if (f == 1 || (f == 0 && pruned)) emit_m = 1;        // forced M2L on a pruned node: src/remotes.c:442
-                else if (f == 0) {
-                    npush = 2;
-                    p0 = (unsigned)a.son[2 * (size_t)jm] | imgbits; p1 = (unsigned)a.son[2 * (size_t)jm + 1] | imgbits;
-                }
-            }
-        }
-        visits += k;
-        __syncwarp();
-        const unsigned m2 = __ballot_sync(0xffffffffu, npush == 2);
-        int pos0 = sbase + 2 * __popc(m2 & lt_mask);
-        const int newsize = sbase + 2 * __popc(m2);
-        if (newsize > STACK_CAP) { err = 1; return false; }
-        if (npush == 2) { stack[pos0] = p0; stack[pos0 + 1] = p1; }
-        ssize = newsize;
-        const unsigned mp = __ballot_sync(0xffffffffu, emit_p);
-        if (emit_p) {
-            const int at = (qtail + __popc(mp & lt_mask)) & (SRCQ_CAP - 1);
-            if (MODE == 0) *reinterpret_cast<int4 *>(&tileq[at]) = ent;
-            else *reinterpret_cast<int4 *>(&srcq[at]) = ent;
-        }
-        qtail += __popc(mp);
-        npairs += __popc(mp);
-        emit_m2l_pairs(a, lane, lt_mask, emit_m, (unsigned)leaf, jme);
-        __syncwarp();
-        return true;
-    };
-    // walk until a batch of source leaves is queued, evaluate the batch whose tiles were requested one round
-    // earlier, request the tiles of the new batch, walk on
-    constexpr int QBATCH = MODE == 0 ? BATCH : 32;
-    bool walking = true;
-    while (true) {
-        while (walking && qtail - qhead < QBATCH) walking = walk_step();
-        if (MODE == 0 && inflight) compute_batch();
-        const int avail = qtail - qhead;
-        if (avail == 0 || err) break;                                // walking implies avail >= QBATCH
-        if (MODE == 0) {
-            int cnt = BATCH;
-            if (avail < BATCH) {                                       // the last batch: pad its last stage with the padding tile
-                cnt = ((avail + NSL - 1) / NSL) * NSL;
-                if (lane < cnt - avail) *reinterpret_cast<int4 *>(&tileq[(qtail + lane) & (SRCQ_CAP - 1)]) = make_int4(a.pad_tile, 0, 0, 0);
-                qtail = qhead + cnt;
-                __syncwarp();
-            }
-            issue_batch(cnt);
-        } else {
-            drain(walking ? qhead + (avail / NSL) * NSL : qtail);
-        }
-    }
-    if (err) { if (lane == 0) atomicOr(&a.counters[3], 1ULL); return; }
-
-    // ---- results ----
-    if (MODE == 0) {
-        float ax, ay, az, hi;
-        unpk2(sk.ax, ax, hi); ax += hi;
-        unpk2(sk.ay, ay, hi); ay += hi;
-        unpk2(sk.az, az, hi); az += hi;
-#pragma unroll
-        for (int m = SW; m < 32; m <<= 1) {
-            ax += __shfl_xor_sync(0xffffffffu, ax, m);
-            ay += __shfl_xor_sync(0xffffffffu, ay, m);
-            az += __shfl_xor_sync(0xffffffffu, az, m);
-        }
-        if (q == 0 && j < sd.npart) {
-            const double sc = pc.mass * pc.inv2rs * pc.inv2rs;
-            double *o = a.acc + 3 * (size_t)(sd.first + j);
-            o[0] += (double)ax * sc; o[1] += (double)ay * sc; o[2] += (double)az * sc;
-        }
-    } else if (MODE == 1) {
+    while (w.step(a, pc, lane))
+        if (w.qtail - qhead >= 32) drain(qhead + ((w.qtail - qhead) / NSL) * NSL);
+    if (w.qtail > qhead) drain(w.qtail);
+    if (w.err) { if (lane == 0) atomicOr(&a.counters[3], 1ULL); return; }
+    if (MODE == 1) {
 #pragma unroll
         for (int m = SW; m < 32; m <<= 1) {
             axd += __shfl_xor_sync(0xffffffffu, axd, m);
@@ -536,19 +450,228 @@ walk_fused_kernel(WalkArgs a, P2PConst pc) {
             double *o = a.acc + 3 * (size_t)(sd.first + j);
             o[0] += axd; o[1] += ayd; o[2] += azd;
         }
-    } else {
-        if (a.pass == 0 && lane == 0) a.lst_off[leaf] = (long)npairs;
-    }
-    if (MODE != 2) {
+        unsigned nsrc = w.nsrc;
 #pragma unroll
         for (int m = 1; m < 32; m <<= 1) nsrc += __shfl_xor_sync(0xffffffffu, nsrc, m);
         if (lane == 0) {
             atomicAdd(&a.counters[0], (unsigned long long)nsrc * (unsigned long long)sd.npart);
-            atomicAdd(&a.counters[2], (unsigned long long)npairs);
-            atomicAdd(&a.counters[4], (unsigned long long)visits);
+            atomicAdd(&a.counters[2], (unsigned long long)w.npairs);
+            atomicAdd(&a.counters[4], (unsigned long long)w.visits);
+        }
+    } else if (a.pass == 0 && lane == 0) {
+        a.lst_off[leaf] = (long)w.npairs;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP32 product kernel: warp-specialised, persistent.
+// ------------------------------------------------------------------------------------------------
+// Sources are read as LEAF TILES: every leaf owns one tile of SW slots in HBM, already in the packed-pair layout of
+// the P2P loop (pn2_p2p.cuh: SW/2 pairs of {x0 x1 y0 y1 | z0 z1 w0 w1}, leaf-centre-relative, units of 2 rs, unused
+// slots = far-away zero-weight padding), so staging a source leaf is a plain 16 * SW byte copy (cp.async, no
+// registers, no arithmetic) and the per-leaf centre offset is applied on the SINK side (3 FADD per lane and stage).
+//
+// A CTA is WS_PAIRS (walker warp, P2P warp) pairs.  The walker takes the next sink leaf from a global ticket
+// counter, resolves its frontier (LeafWalk) and, whenever BATCH source leaves are queued, requests their tiles with
+// cp.async into the next slot of a ring in shared memory; the copies' completion and the slot header are published
+// through an mbarrier.  The P2P warp only waits for full slots and evaluates them: it never touches the tree, keeps
+// a large register budget (setmaxnreg) for instruction-level parallelism across source pairs, and with only two or
+// three such warps per scheduler the operand-reuse caches survive (measured in tools/ubench: 2 warps per scheduler
+// with 250 registers reach 0.83 of the FMA peak in this loop, 8 warps with 64 registers 0.70).
+#ifndef WS_PAIRS
+#define WS_PAIRS 4
+#endif
+#ifndef WS_SLOTS
+#define WS_SLOTS 2
+#endif
+#ifndef WS_CTAS_PER_SM
+#define WS_CTAS_PER_SM 2
+#endif
+#ifndef WS_U
+#define WS_U 2                    // stack entries per lane and walker step
+#endif
+#define WS_QCAP (WS_U == 1 ? 64 : (WS_U == 2 ? 128 : 256))     // >= BATCH - 1 + 32 WS_U queued source leaves
+#ifndef WS_REGS_WALK
+#define WS_REGS_WALK 88
+#endif
+#ifndef WS_REGS_P2P
+#define WS_REGS_P2P 168
+#endif
+
+template <int SW>
+struct WsLayout {
+    static constexpr int NSL = 32 / SW;
+    static constexpr int NST = 8;                         // stages per batch
+    static constexpr int BATCH = NST * NSL;               // source leaves per batch (32 / 16 / 8)
+    static constexpr int TB = 16 * SW;                    // tile bytes
+    static constexpr int ROWB = TB + 16;                  // row stride: the 16 spare bytes hold the leaf's {tile, dx, dy, dz}
+                                                          // and de-conflict the NSL broadcast rows
+    static constexpr int SLOT_BYTES = BATCH * ROWB + 32;  // rows + header {leaf, count, last, first | npart, ...}
+    static constexpr int PAIR_BYTES = WS_SLOTS * SLOT_BYTES + STACK_CAP * 4 + WS_QCAP * 16 + 64 /* sink geometry */
+                                      + WS_SLOTS * 16 /* mbarriers full, empty */;
+    static constexpr int CTA_BYTES = WS_PAIRS * PAIR_BYTES;
+};
+
+__device__ __forceinline__ void cp_async16(unsigned dst_shared, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst_shared), "l"(src) : "memory");
+}
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(bar) : "memory");
+}
+// arrive on `bar` once all cp.async of this thread issued so far have landed (does not change the pending count)
+__device__ __forceinline__ void mbar_arrive_on_copies(unsigned bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned done;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+
+template <int SW, bool LS>
+__global__ void __launch_bounds__(WS_PAIRS * 64, WS_CTAS_PER_SM) walk_p2p_ws_kernel(WalkArgs a, P2PConst pc) {
+    using WL = WsLayout<SW>;
+    constexpr int NSL = WL::NSL, NST = WL::NST, BATCH = WL::BATCH, TB = WL::TB, ROWB = WL::ROWB;
+    extern __shared__ __align__(16) unsigned char ws_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool is_p2p = warp < WS_PAIRS;                        // warps 0..WS_PAIRS-1: P2P, the rest: walkers
+    const int pair = is_p2p ? warp : warp - WS_PAIRS;
+    unsigned char *base = ws_smem + pair * WL::PAIR_BYTES;
+    unsigned char *slots = base;
+    unsigned *stack = reinterpret_cast<unsigned *>(base + WS_SLOTS * WL::SLOT_BYTES);
+    int4 *queue = reinterpret_cast<int4 *>(base + WS_SLOTS * WL::SLOT_BYTES + STACK_CAP * 4);
+    double *sink_g = reinterpret_cast<double *>(base + WS_SLOTS * WL::SLOT_BYTES + STACK_CAP * 4 + WS_QCAP * 16);
+    const unsigned bar0 = (unsigned)__cvta_generic_to_shared(base + WS_SLOTS * WL::SLOT_BYTES + STACK_CAP * 4 + WS_QCAP * 16 + 64);
+    // full[s] = bar0 + 16 s (32 copy arrivals + 1 header arrival), empty[s] = bar0 + 16 s + 8 (1 arrival)
+    if (!is_p2p && lane == 0)
+        for (int s = 0; s < WS_SLOTS; s++) { mbar_init(bar0 + 16 * s, 33); mbar_init(bar0 + 16 * s + 8, 1); }
+    __syncthreads();
+    const int q = lane / SW, j = lane % SW;
+
+    if (!is_p2p) {
+        // ================= walker =================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_REGS_WALK));
+        const unsigned slot_dst = (unsigned)__cvta_generic_to_shared(slots) + q * ROWB + j * 16;   // this lane's chunk of row q
+        const char *tile_src = reinterpret_cast<const char *>(a.tiles) + j * 16;
+        unsigned long long tot_int = 0, tot_pairs = 0, tot_visits = 0;
+        int slot = 0;
+        unsigned empty_par = (1u << WS_SLOTS) - 1;          // a fresh barrier passes a wait on parity 1
+        int any_err = 0;
+        LeafWalk<0, WS_U, WS_QCAP> w;
+        while (true) {
+            int leaf = 0;
+            if (lane == 0) leaf = (int)atomicAdd(&a.counters[5], 1ULL);
+            leaf = __shfl_sync(0xffffffffu, leaf, 0);
+            const bool finished = leaf >= a.nleaf;
+            int qhead = 0;
+            bool walking = !finished;
+            if (!finished) w.begin(a, leaf, stack, queue, sink_g, lane);
+            while (true) {
+                while (walking && w.qtail - qhead < BATCH) walking = w.step(a, pc, lane);
+                const int avail = finished ? 0 : w.qtail - qhead;      // >= BATCH, or the walk is over
+                const bool is_last = !walking && avail <= BATCH;
+                const int cnt = avail < BATCH ? avail : BATCH;
+                const int padded = ((cnt + NSL - 1) / NSL) * NSL;      // only the last batch can be ragged
+                if (lane < padded - cnt) queue[(qhead + cnt + lane) & (WS_QCAP - 1)] = make_int4(a.pad_tile, 0, 0, 0);
+                __syncwarp();
+                // wait until the P2P warp has released this slot, then fill it
+                mbar_wait(bar0 + 16 * slot + 8, (empty_par >> slot) & 1u);
+                empty_par ^= 1u << slot;
+                unsigned char *sl = slots + slot * WL::SLOT_BYTES;
+#pragma unroll
+                for (int s = 0; s < NST; s++) {
+                    if (s * NSL < padded) {
+                        const int4 e = queue[(qhead + s * NSL + q) & (WS_QCAP - 1)];
+                        cp_async16(slot_dst + slot * WL::SLOT_BYTES + s * NSL * ROWB, tile_src + (size_t)e.x * TB);
+                        if (j == 0) *reinterpret_cast<int4 *>(sl + (s * NSL + q) * ROWB + TB) = e;
+                    }
+                }
+                if (lane == 0)
+                    *reinterpret_cast<int4 *>(sl + BATCH * ROWB) = make_int4(finished ? -1 : leaf, padded, is_last ? 1 : 0, finished ? 0 : (w.sd.first));
+                if (lane == 1) *reinterpret_cast<int *>(sl + BATCH * ROWB + 16) = finished ? 0 : w.sd.npart;
+                mbar_arrive_on_copies(bar0 + 16 * slot);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar0 + 16 * slot);
+                qhead += cnt;
+                slot = slot + 1 == WS_SLOTS ? 0 : slot + 1;
+                if (is_last) break;
+            }
+            if (finished) break;
+            unsigned nsrc = w.nsrc;
+#pragma unroll
+            for (int m = 1; m < 32; m <<= 1) nsrc += __shfl_xor_sync(0xffffffffu, nsrc, m);
+            tot_int += (unsigned long long)nsrc * (unsigned long long)w.sd.npart;
+            tot_pairs += w.npairs; tot_visits += w.visits;
+            any_err |= w.err;
+        }
+        if (lane == 0) {
+            atomicAdd(&a.counters[0], tot_int);
+            atomicAdd(&a.counters[2], tot_pairs);
+            atomicAdd(&a.counters[4], tot_visits);
+            if (any_err) atomicOr(&a.counters[3], 1ULL);
+        }
+    } else {
+        // ================= P2P =================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WS_REGS_P2P));
+        const float inv_eps = pc.inv_eps;
+        const double sc = pc.mass * pc.inv2rs * pc.inv2rs;
+        int slot = 0, cur = -1;
+        unsigned full_par = 0;
+        float xi = 0.f, yi = 0.f, zi = 0.f;
+        P2PSinkPk sk;
+        sk.nx = sk.ny = sk.nz = sk.ax = sk.ay = sk.az = pk2(0.f, 0.f);
+        while (true) {
+            mbar_wait(bar0 + 16 * slot, (full_par >> slot) & 1u);
+            full_par ^= 1u << slot;
+            const unsigned char *sl = slots + slot * WL::SLOT_BYTES;
+            const int4 hdr = *reinterpret_cast<const int4 *>(sl + BATCH * ROWB);
+            const int npart = *reinterpret_cast<const int *>(sl + BATCH * ROWB + 16);
+            if (hdr.x < 0) break;
+            if (hdr.x != cur) {                    // a new sink leaf: slot j of its own tile (padding slots compute, never written)
+                cur = hdr.x;
+                const float *t = a.tiles + (size_t)cur * (4 * SW) + (j >> 1) * 8 + (j & 1);
+                xi = t[0]; yi = t[2]; zi = t[4];
+                sk.ax = sk.ay = sk.az = pk2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int s = 0; s < NST; s++) {
+                if (s * NSL < hdr.y) {
+                    const float *row = reinterpret_cast<const float *>(sl + (s * NSL + q) * ROWB);
+                    const float4 o = *reinterpret_cast<const float4 *>(row + TB / 4);
+                    const float nx = o.y - xi, ny = o.z - yi, nz = o.w - zi;          // x_j + (centre offset - x_i)
+                    sk.nx = pk2(nx, nx); sk.ny = pk2(ny, ny); sk.nz = pk2(nz, nz);
+                    pk_row<SW, LS>(row, 0, sk, inv_eps);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar0 + 16 * slot + 8);          // the slot is free
+            slot = slot + 1 == WS_SLOTS ? 0 : slot + 1;
+            if (hdr.z) {                           // last batch of this sink leaf: reduce the slices, write
+                float ax, ay, az, hi;
+                unpk2(sk.ax, ax, hi); ax += hi;
+                unpk2(sk.ay, ay, hi); ay += hi;
+                unpk2(sk.az, az, hi); az += hi;
+#pragma unroll
+                for (int m = SW; m < 32; m <<= 1) {
+                    ax += __shfl_xor_sync(0xffffffffu, ax, m);
+                    ay += __shfl_xor_sync(0xffffffffu, ay, m);
+                    az += __shfl_xor_sync(0xffffffffu, az, m);
+                }
+                if (q == 0 && j < npart) {
+                    double *o = a.acc + 3 * (size_t)(hdr.w + j);
+                    o[0] += (double)ax * sc; o[1] += (double)ay * sc; o[2] += (double)az * sc;
+                }
+                cur = -1;
+            }
         }
     }
 }
+
 
 // Leaf tiles (FP32 mode): slot j of tile t <- particle j of the leaf, packed-pair layout; tile nt = all padding.
 // Tiles 0..nleaf-1 are the local leaves, nleaf.. the received LET leaves (cells rleaf0..).
@@ -568,13 +691,25 @@ __global__ void tile_kernel(int nt, int nleaf, int rleaf0, const LeafDesc *__res
 }
 
 template <int SW>
-static void launch_mode(pn2_ctx *h, const WalkArgs &a, int mode) {
-    unsigned grid = (unsigned)((a.nleaf + WALK_WARPS - 1) / WALK_WARPS);
-    if (mode == 0 && h->prm.longshort) walk_fused_kernel<SW, 0, true><<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
-    else if (mode == 0) walk_fused_kernel<SW, 0, false><<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
-    else if (mode == 1) walk_fused_kernel<SW, 1, true><<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
-    else walk_fused_kernel<SW, 2, true><<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
+static int launch_mode(pn2_ctx *h, const WalkArgs &a, int mode) {
+    if (mode == 0) {
+        // persistent, warp-specialised: WS_CTAS_PER_SM CTAs per SM, sink leaves handed out by ticket (counters[5])
+        const int smem = WsLayout<SW>::CTA_BYTES;
+        const unsigned grid = (unsigned)(WS_CTAS_PER_SM * h->sm_count);
+        if (h->prm.longshort) {
+            CUDA_TRY(cudaFuncSetAttribute(walk_p2p_ws_kernel<SW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            walk_p2p_ws_kernel<SW, true><<<grid, WS_PAIRS * 64, smem, h->stream>>>(a, h->pc);
+        } else {
+            CUDA_TRY(cudaFuncSetAttribute(walk_p2p_ws_kernel<SW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            walk_p2p_ws_kernel<SW, false><<<grid, WS_PAIRS * 64, smem, h->stream>>>(a, h->pc);
+        }
+    } else {
+        const unsigned grid = (unsigned)((a.nleaf + WALK_WARPS - 1) / WALK_WARPS);
+        if (mode == 1) walk_leaf_kernel<SW, 1><<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
+        else walk_leaf_kernel<SW, 2><<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
+    }
     h->launches++;
+    return PN2_OK;
 }
 
 static void fill_args(pn2_ctx *h, WalkArgs &a) {
@@ -637,9 +772,10 @@ int pn2_walk_fused(pn2_ctx *h, int dump) {
         h->launches++;
         a.tiles = h->tiles.p; a.pad_tile = nt;
     }
-    if (ml <= 8) launch_mode<8>(h, a, mode);
-    else if (ml <= 16) launch_mode<16>(h, a, mode);
-    else launch_mode<32>(h, a, mode);
+    if (mode == 0) CUDA_TRY(cudaMemsetAsync(h->counters.p + 5, 0, sizeof(unsigned long long), h->stream));   // leaf tickets
+    if (ml <= 8) PN2_TRY(launch_mode<8>(h, a, mode));
+    else if (ml <= 16) PN2_TRY(launch_mode<16>(h, a, mode));
+    else PN2_TRY(launch_mode<32>(h, a, mode));
     KERNEL_CHECK();
     return PN2_OK;
 }
