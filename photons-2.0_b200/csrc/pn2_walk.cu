@@ -464,214 +464,138 @@ __global__ void __launch_bounds__(WALK_WARPS * 32) walk_leaf_kernel(WalkArgs a, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// FP32 product kernel: warp-specialised, persistent.
+// FP32 product kernel: one warp per sink leaf, list walk fused with the P2P evaluation
 // ------------------------------------------------------------------------------------------------
 // Sources are read as LEAF TILES: every leaf owns one tile of SW slots in HBM, already in the packed-pair layout of
 // the P2P loop (pn2_p2p.cuh: SW/2 pairs of {x0 x1 y0 y1 | z0 z1 w0 w1}, leaf-centre-relative, units of 2 rs, unused
-// slots = far-away zero-weight padding), so staging a source leaf is a plain 16 * SW byte copy (cp.async, no
-// registers, no arithmetic) and the per-leaf centre offset is applied on the SINK side (3 FADD per lane and stage).
-//
-// A CTA is WS_PAIRS (walker warp, P2P warp) pairs.  The walker takes the next sink leaf from a global ticket
-// counter, resolves its frontier (LeafWalk) and, whenever BATCH source leaves are queued, requests their tiles with
-// cp.async into the next slot of a ring in shared memory; the copies' completion and the slot header are published
-// through an mbarrier.  The P2P warp only waits for full slots and evaluates them: it never touches the tree, keeps
-// a large register budget (setmaxnreg) for instruction-level parallelism across source pairs, and with only two or
-// three such warps per scheduler the operand-reuse caches survive (measured in tools/ubench: 2 warps per scheduler
-// with 250 registers reach 0.83 of the FMA peak in this loop, 8 warps with 64 registers 0.70).
-#ifndef WS_PAIRS
-#define WS_PAIRS 4
-#endif
-#ifndef WS_SLOTS
-#define WS_SLOTS 2
-#endif
-#ifndef WS_CTAS_PER_SM
-#define WS_CTAS_PER_SM 2
-#endif
-#ifndef WS_U
-#define WS_U 2                    // stack entries per lane and walker step
-#endif
-#define WS_QCAP (WS_U == 1 ? 64 : (WS_U == 2 ? 128 : 256))     // >= BATCH - 1 + 32 WS_U queued source leaves
-#ifndef WS_REGS_WALK
-#define WS_REGS_WALK 88
-#endif
-#ifndef WS_REGS_P2P
-#define WS_REGS_P2P 168
-#endif
-
+// slots = far-away zero-weight padding), so staging a source leaf is a plain 16 * SW byte copy: the warp issues
+// cp.async (LDGSTS.128: no registers, no arithmetic) for a whole BATCH of queued leaves at once and goes on walking
+// while the copies land; the per-leaf centre offset is applied on the SINK side (3 FADD per lane and stage).
+// (A warp-specialised persistent variant -- walker warps feeding P2P warps through an mbarrier ring, setmaxnreg --
+// was built and measured slower, 61.5 vs 48.1 ms at 256^3: one latency-bound walker cannot feed one P2P warp, see
+// DESIGN.md 4.3.)
 template <int SW>
-struct WsLayout {
+struct FusedLayout {
     static constexpr int NSL = 32 / SW;
     static constexpr int NST = 8;                         // stages per batch
     static constexpr int BATCH = NST * NSL;               // source leaves per batch (32 / 16 / 8)
     static constexpr int TB = 16 * SW;                    // tile bytes
     static constexpr int ROWB = TB + 16;                  // row stride: the 16 spare bytes hold the leaf's {tile, dx, dy, dz}
                                                           // and de-conflict the NSL broadcast rows
-    static constexpr int SLOT_BYTES = BATCH * ROWB + 32;  // rows + header {leaf, count, last, first | npart, ...}
-    static constexpr int PAIR_BYTES = WS_SLOTS * SLOT_BYTES + STACK_CAP * 4 + WS_QCAP * 16 + 64 /* sink geometry */
-                                      + WS_SLOTS * 16 /* mbarriers full, empty */;
-    static constexpr int CTA_BYTES = WS_PAIRS * PAIR_BYTES;
+    static constexpr int STAGE_BYTES = BATCH * ROWB;
 };
 
 __device__ __forceinline__ void cp_async16(unsigned dst_shared, const void *src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst_shared), "l"(src) : "memory");
 }
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned bar) {
-    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(bar) : "memory");
-}
-// arrive on `bar` once all cp.async of this thread issued so far have landed (does not change the pending count)
-__device__ __forceinline__ void mbar_arrive_on_copies(unsigned bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-    unsigned done;
-    do {
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    } while (!done);
-}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-template <int SW, bool LS>
-__global__ void __launch_bounds__(WS_PAIRS * 64, WS_CTAS_PER_SM) walk_p2p_ws_kernel(WalkArgs a, P2PConst pc) {
-    using WL = WsLayout<SW>;
-    constexpr int NSL = WL::NSL, NST = WL::NST, BATCH = WL::BATCH, TB = WL::TB, ROWB = WL::ROWB;
-    extern __shared__ __align__(16) unsigned char ws_smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bool is_p2p = warp < WS_PAIRS;                        // warps 0..WS_PAIRS-1: P2P, the rest: walkers
-    const int pair = is_p2p ? warp : warp - WS_PAIRS;
-    unsigned char *base = ws_smem + pair * WL::PAIR_BYTES;
-    unsigned char *slots = base;
-    unsigned *stack = reinterpret_cast<unsigned *>(base + WS_SLOTS * WL::SLOT_BYTES);
-    int4 *queue = reinterpret_cast<int4 *>(base + WS_SLOTS * WL::SLOT_BYTES + STACK_CAP * 4);
-    double *sink_g = reinterpret_cast<double *>(base + WS_SLOTS * WL::SLOT_BYTES + STACK_CAP * 4 + WS_QCAP * 16);
-    const unsigned bar0 = (unsigned)__cvta_generic_to_shared(base + WS_SLOTS * WL::SLOT_BYTES + STACK_CAP * 4 + WS_QCAP * 16 + 64);
-    // full[s] = bar0 + 16 s (32 copy arrivals + 1 header arrival), empty[s] = bar0 + 16 s + 8 (1 arrival)
-    if (!is_p2p && lane == 0)
-        for (int s = 0; s < WS_SLOTS; s++) { mbar_init(bar0 + 16 * s, 33); mbar_init(bar0 + 16 * s + 8, 1); }
-    __syncthreads();
+template <int SW, bool LS>      // LS: with the long/short split factor g(r / 2rs)
+__global__ void __launch_bounds__(WALK_WARPS * 32, LEAF_MIN_BLOCKS) walk_fused_kernel(WalkArgs a, P2PConst pc) {
+    using FL = FusedLayout<SW>;
+    constexpr int NSL = FL::NSL, NST = FL::NST, BATCH = FL::BATCH, TB = FL::TB, ROWB = FL::ROWB;
+    __shared__ unsigned s_stack[WALK_WARPS][STACK_CAP];
+    __shared__ int4 s_srcq[WALK_WARPS][SRCQ_CAP];
+    __shared__ __align__(16) unsigned char s_stage[WALK_WARPS][FL::STAGE_BYTES];
+    __shared__ double s_sink[WALK_WARPS][6];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int leaf = blockIdx.x * WALK_WARPS + wib;
+    if (leaf >= a.nleaf) return;
     const int q = lane / SW, j = lane % SW;
+    LeafWalk<0, 1, SRCQ_CAP> w;
+    w.begin(a, leaf, s_stack[wib], s_srcq[wib], s_sink[wib], lane);
+    // sink: slot j of the leaf's own tile (padding slots compute, but are never written)
+    float xi, yi, zi;
+    {
+        const float *t = a.tiles + (size_t)leaf * (4 * SW) + (j >> 1) * 8 + (j & 1);
+        xi = t[0]; yi = t[2]; zi = t[4];
+    }
+    P2PSinkPk sk;
+    sk.nx = sk.ny = sk.nz = sk.ax = sk.ay = sk.az = pk2(0.f, 0.f);
+    const float inv_eps = pc.inv_eps;
 
-    if (!is_p2p) {
-        // ================= walker =================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_REGS_WALK));
-        const unsigned slot_dst = (unsigned)__cvta_generic_to_shared(slots) + q * ROWB + j * 16;   // this lane's chunk of row q
-        const char *tile_src = reinterpret_cast<const char *>(a.tiles) + j * 16;
-        unsigned long long tot_int = 0, tot_pairs = 0, tot_visits = 0;
-        int slot = 0;
-        unsigned empty_par = (1u << WS_SLOTS) - 1;          // a fresh barrier passes a wait on parity 1
-        int any_err = 0;
-        LeafWalk<0, WS_U, WS_QCAP> w;
-        while (true) {
-            int leaf = 0;
-            if (lane == 0) leaf = (int)atomicAdd(&a.counters[5], 1ULL);
-            leaf = __shfl_sync(0xffffffffu, leaf, 0);
-            const bool finished = leaf >= a.nleaf;
-            int qhead = 0;
-            bool walking = !finished;
-            if (!finished) w.begin(a, leaf, stack, queue, sink_g, lane);
-            while (true) {
-                while (walking && w.qtail - qhead < BATCH) walking = w.step(a, pc, lane);
-                const int avail = finished ? 0 : w.qtail - qhead;      // >= BATCH, or the walk is over
-                const bool is_last = !walking && avail <= BATCH;
-                const int cnt = avail < BATCH ? avail : BATCH;
-                const int padded = ((cnt + NSL - 1) / NSL) * NSL;      // only the last batch can be ragged
-                if (lane < padded - cnt) queue[(qhead + cnt + lane) & (WS_QCAP - 1)] = make_int4(a.pad_tile, 0, 0, 0);
-                __syncwarp();
-                // wait until the P2P warp has released this slot, then fill it
-                mbar_wait(bar0 + 16 * slot + 8, (empty_par >> slot) & 1u);
-                empty_par ^= 1u << slot;
-                unsigned char *sl = slots + slot * WL::SLOT_BYTES;
+    int qhead = 0, inflight = 0;
+    unsigned char *stage = s_stage[wib];
+    const unsigned stage_dst = (unsigned)__cvta_generic_to_shared(stage) + q * ROWB + j * 16;   // this lane's 16-byte chunk of row q
+    const char *tile_src = reinterpret_cast<const char *>(a.tiles) + j * 16;
+    auto issue_batch = [&](int cnt) {      // cnt <= BATCH queue entries from qhead, a multiple of NSL
 #pragma unroll
-                for (int s = 0; s < NST; s++) {
-                    if (s * NSL < padded) {
-                        const int4 e = queue[(qhead + s * NSL + q) & (WS_QCAP - 1)];
-                        cp_async16(slot_dst + slot * WL::SLOT_BYTES + s * NSL * ROWB, tile_src + (size_t)e.x * TB);
-                        if (j == 0) *reinterpret_cast<int4 *>(sl + (s * NSL + q) * ROWB + TB) = e;
-                    }
-                }
-                if (lane == 0)
-                    *reinterpret_cast<int4 *>(sl + BATCH * ROWB) = make_int4(finished ? -1 : leaf, padded, is_last ? 1 : 0, finished ? 0 : (w.sd.first));
-                if (lane == 1) *reinterpret_cast<int *>(sl + BATCH * ROWB + 16) = finished ? 0 : w.sd.npart;
-                mbar_arrive_on_copies(bar0 + 16 * slot);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar0 + 16 * slot);
-                qhead += cnt;
-                slot = slot + 1 == WS_SLOTS ? 0 : slot + 1;
-                if (is_last) break;
+        for (int s = 0; s < NST; s++) {
+            if (s * NSL < cnt) {
+                const int4 e = w.queue[(qhead + s * NSL + q) & (SRCQ_CAP - 1)];
+                cp_async16(stage_dst + s * NSL * ROWB, tile_src + (size_t)e.x * TB);
+                if (j == 0) *reinterpret_cast<int4 *>(stage + (s * NSL + q) * ROWB + TB) = e;
             }
-            if (finished) break;
-            unsigned nsrc = w.nsrc;
-#pragma unroll
-            for (int m = 1; m < 32; m <<= 1) nsrc += __shfl_xor_sync(0xffffffffu, nsrc, m);
-            tot_int += (unsigned long long)nsrc * (unsigned long long)w.sd.npart;
-            tot_pairs += w.npairs; tot_visits += w.visits;
-            any_err |= w.err;
         }
-        if (lane == 0) {
-            atomicAdd(&a.counters[0], tot_int);
-            atomicAdd(&a.counters[2], tot_pairs);
-            atomicAdd(&a.counters[4], tot_visits);
-            if (any_err) atomicOr(&a.counters[3], 1ULL);
-        }
-    } else {
-        // ================= P2P =================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WS_REGS_P2P));
-        const float inv_eps = pc.inv_eps;
-        const double sc = pc.mass * pc.inv2rs * pc.inv2rs;
-        int slot = 0, cur = -1;
-        unsigned full_par = 0;
-        float xi = 0.f, yi = 0.f, zi = 0.f;
-        P2PSinkPk sk;
-        sk.nx = sk.ny = sk.nz = sk.ax = sk.ay = sk.az = pk2(0.f, 0.f);
-        while (true) {
-            mbar_wait(bar0 + 16 * slot, (full_par >> slot) & 1u);
-            full_par ^= 1u << slot;
-            const unsigned char *sl = slots + slot * WL::SLOT_BYTES;
-            const int4 hdr = *reinterpret_cast<const int4 *>(sl + BATCH * ROWB);
-            const int npart = *reinterpret_cast<const int *>(sl + BATCH * ROWB + 16);
-            if (hdr.x < 0) break;
-            if (hdr.x != cur) {                    // a new sink leaf: slot j of its own tile (padding slots compute, never written)
-                cur = hdr.x;
-                const float *t = a.tiles + (size_t)cur * (4 * SW) + (j >> 1) * 8 + (j & 1);
-                xi = t[0]; yi = t[2]; zi = t[4];
-                sk.ax = sk.ay = sk.az = pk2(0.f, 0.f);
-            }
+        cp_async_commit();
+        inflight = cnt;
+        qhead += cnt;
+    };
+    auto compute_stage = [&](int s) {
+        const float *row = reinterpret_cast<const float *>(stage + (s * NSL + q) * ROWB);
+        const float4 o = *reinterpret_cast<const float4 *>(row + TB / 4);
+        const float nx = o.y - xi, ny = o.z - yi, nz = o.w - zi;          // x_j + (centre offset - x_i)
+        sk.nx = pk2(nx, nx); sk.ny = pk2(ny, ny); sk.nz = pk2(nz, nz);
+        pk_row<SW, LS>(row, 0, sk, inv_eps);
+    };
+    auto compute_batch = [&]() {
+        cp_async_wait_all();
+        __syncwarp();
+        if (inflight == BATCH) {           // the common case as one straight-line block: stages overlap in the schedule
 #pragma unroll
-            for (int s = 0; s < NST; s++) {
-                if (s * NSL < hdr.y) {
-                    const float *row = reinterpret_cast<const float *>(sl + (s * NSL + q) * ROWB);
-                    const float4 o = *reinterpret_cast<const float4 *>(row + TB / 4);
-                    const float nx = o.y - xi, ny = o.z - yi, nz = o.w - zi;          // x_j + (centre offset - x_i)
-                    sk.nx = pk2(nx, nx); sk.ny = pk2(ny, ny); sk.nz = pk2(nz, nz);
-                    pk_row<SW, LS>(row, 0, sk, inv_eps);
-                }
-            }
+            for (int s = 0; s < NST; s++) compute_stage(s);
+        } else {
+#pragma unroll 1
+            for (int s = 0; s * NSL < inflight; s++) compute_stage(s);
+        }
+        inflight = 0;
+        __syncwarp();                      // the stage is free for the next batch
+    };
+    // walk until a batch of source leaves is queued, evaluate the batch whose tiles were requested one round
+    // earlier, request the tiles of the new batch, walk on
+    bool walking = true;
+    while (true) {
+        while (walking && w.qtail - qhead < BATCH) walking = w.step(a, pc, lane);
+        if (inflight) compute_batch();
+        const int avail = w.qtail - qhead;
+        if (avail == 0 || w.err) break;                              // walking implies avail >= BATCH
+        int cnt = BATCH;
+        if (avail < BATCH) {                                           // the last batch: pad its last stage with the padding tile
+            cnt = ((avail + NSL - 1) / NSL) * NSL;
+            if (lane < cnt - avail) w.queue[(w.qtail + lane) & (SRCQ_CAP - 1)] = make_int4(a.pad_tile, 0, 0, 0);
+            w.qtail = qhead + cnt;
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar0 + 16 * slot + 8);          // the slot is free
-            slot = slot + 1 == WS_SLOTS ? 0 : slot + 1;
-            if (hdr.z) {                           // last batch of this sink leaf: reduce the slices, write
-                float ax, ay, az, hi;
-                unpk2(sk.ax, ax, hi); ax += hi;
-                unpk2(sk.ay, ay, hi); ay += hi;
-                unpk2(sk.az, az, hi); az += hi;
-#pragma unroll
-                for (int m = SW; m < 32; m <<= 1) {
-                    ax += __shfl_xor_sync(0xffffffffu, ax, m);
-                    ay += __shfl_xor_sync(0xffffffffu, ay, m);
-                    az += __shfl_xor_sync(0xffffffffu, az, m);
-                }
-                if (q == 0 && j < npart) {
-                    double *o = a.acc + 3 * (size_t)(hdr.w + j);
-                    o[0] += (double)ax * sc; o[1] += (double)ay * sc; o[2] += (double)az * sc;
-                }
-                cur = -1;
-            }
         }
+        issue_batch(cnt);
+    }
+    if (w.err) { if (lane == 0) atomicOr(&a.counters[3], 1ULL); return; }
+
+    float ax, ay, az, hi;
+    unpk2(sk.ax, ax, hi); ax += hi;
+    unpk2(sk.ay, ay, hi); ay += hi;
+    unpk2(sk.az, az, hi); az += hi;
+#pragma unroll
+    for (int m = SW; m < 32; m <<= 1) {
+        ax += __shfl_xor_sync(0xffffffffu, ax, m);
+        ay += __shfl_xor_sync(0xffffffffu, ay, m);
+        az += __shfl_xor_sync(0xffffffffu, az, m);
+    }
+    const LeafDesc sd = w.sd;
+    if (q == 0 && j < sd.npart) {
+        const double sc = pc.mass * pc.inv2rs * pc.inv2rs;
+        double *o = a.acc + 3 * (size_t)(sd.first + j);
+        o[0] += (double)ax * sc; o[1] += (double)ay * sc; o[2] += (double)az * sc;
+    }
+    unsigned nsrc = w.nsrc;
+#pragma unroll
+    for (int m = 1; m < 32; m <<= 1) nsrc += __shfl_xor_sync(0xffffffffu, nsrc, m);
+    if (lane == 0) {
+        atomicAdd(&a.counters[0], (unsigned long long)nsrc * (unsigned long long)sd.npart);
+        atomicAdd(&a.counters[2], (unsigned long long)w.npairs);
+        atomicAdd(&a.counters[4], (unsigned long long)w.visits);
     }
 }
-
 
 // Leaf tiles (FP32 mode): slot j of tile t <- particle j of the leaf, packed-pair layout; tile nt = all padding.
 // Tiles 0..nleaf-1 are the local leaves, nleaf.. the received LET leaves (cells rleaf0..).
@@ -691,25 +615,13 @@ __global__ void tile_kernel(int nt, int nleaf, int rleaf0, const LeafDesc *__res
 }
 
 template <int SW>
-static int launch_mode(pn2_ctx *h, const WalkArgs &a, int mode) {
-    if (mode == 0) {
-        // persistent, warp-specialised: WS_CTAS_PER_SM CTAs per SM, sink leaves handed out by ticket (counters[5])
-        const int smem = WsLayout<SW>::CTA_BYTES;
-        const unsigned grid = (unsigned)(WS_CTAS_PER_SM * h->sm_count);
-        if (h->prm.longshort) {
-            CUDA_TRY(cudaFuncSetAttribute(walk_p2p_ws_kernel<SW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            walk_p2p_ws_kernel<SW, true><<<grid, WS_PAIRS * 64, smem, h->stream>>>(a, h->pc);
-        } else {
-            CUDA_TRY(cudaFuncSetAttribute(walk_p2p_ws_kernel<SW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            walk_p2p_ws_kernel<SW, false><<<grid, WS_PAIRS * 64, smem, h->stream>>>(a, h->pc);
-        }
-    } else {
-        const unsigned grid = (unsigned)((a.nleaf + WALK_WARPS - 1) / WALK_WARPS);
-        if (mode == 1) walk_leaf_kernel<SW, 1><<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
-        else walk_leaf_kernel<SW, 2><<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
-    }
+static void launch_mode(pn2_ctx *h, const WalkArgs &a, int mode) {
+    const unsigned grid = (unsigned)((a.nleaf + WALK_WARPS - 1) / WALK_WARPS);
+    if (mode == 0 && h->prm.longshort) walk_fused_kernel<SW, true><<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
+    else if (mode == 0) walk_fused_kernel<SW, false><<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
+    else if (mode == 1) walk_leaf_kernel<SW, 1><<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
+    else walk_leaf_kernel<SW, 2><<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
     h->launches++;
-    return PN2_OK;
 }
 
 static void fill_args(pn2_ctx *h, WalkArgs &a) {
@@ -772,10 +684,9 @@ int pn2_walk_fused(pn2_ctx *h, int dump) {
         h->launches++;
         a.tiles = h->tiles.p; a.pad_tile = nt;
     }
-    if (mode == 0) CUDA_TRY(cudaMemsetAsync(h->counters.p + 5, 0, sizeof(unsigned long long), h->stream));   // leaf tickets
-    if (ml <= 8) PN2_TRY(launch_mode<8>(h, a, mode));
-    else if (ml <= 16) PN2_TRY(launch_mode<16>(h, a, mode));
-    else PN2_TRY(launch_mode<32>(h, a, mode));
+    if (ml <= 8) launch_mode<8>(h, a, mode);
+    else if (ml <= 16) launch_mode<16>(h, a, mode);
+    else launch_mode<32>(h, a, mode);
     KERNEL_CHECK();
     return PN2_OK;
 }
