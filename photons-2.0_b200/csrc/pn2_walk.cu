@@ -173,6 +173,8 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NODE_MIN_BLOCKS) frontier_nod
     SpanReader rd;
     rd.init(a.spans, im == a.root ? a.root_head : a.o_head[a.parent[im]]);
     int ssize = 0;
+    unsigned pre_e = 0;                      // the next chunk of F(im), requested one step ahead
+    int pre_n = rd.fetch(lane, pre_e);
 
     int osize = 0;
     unsigned first_span = 0, prev_span = 0;
@@ -199,13 +201,11 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NODE_MIN_BLOCKS) frontier_nod
 
     while (true) {
         // refill from the parent's list when the stack runs low
-        if (ssize < 32 && rd.more()) {
-            unsigned e = 0;
-            int n = rd.fetch(lane, e);
-            if (lane < n) stack[ssize + lane] = e;
-            ssize += n;
+        while (ssize < 32 && pre_n > 0) {
+            if (lane < pre_n) stack[ssize + lane] = pre_e;
+            ssize += pre_n;
+            pre_n = rd.fetch(lane, pre_e);
             __syncwarp();
-            if (n > 0 && ssize < 32 && rd.more()) continue;
         }
         if (ssize == 0) break;
         int k = ssize < 32 ? ssize : 32;
@@ -220,12 +220,14 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NODE_MIN_BLOCKS) frontier_nod
             const unsigned img = jme >> PN2_IMG_SHIFT, imgbits = jme & ~PN2_CELL_MASK;
             const bool lj = jm < a.nleaf || (jm >= a.rleaf0 && jm < a.rnode0);
             const bool remote = img != 0 || jm >= a.rleaf0;          // walk_task_*_ext rules (src/remotes.c)
+            // geometry and sons are requested together, before either is used (one round trip per step)
+            double cj[3], wj[3];
+            load_geom(a.geom, jm, cj, wj);
+            const int2 sons = lj ? make_int2(-1, -1) : *reinterpret_cast<const int2 *>(a.son + 2 * (size_t)jm);
             if (img == 0 && jm == im) {
                 // walk(im, im): all four son combinations (src/fmm.c:429-436)
-                no = 2; o0 = (unsigned)a.son[2 * (size_t)im]; o1 = (unsigned)a.son[2 * (size_t)im + 1];
+                no = 2; o0 = (unsigned)sons.x; o1 = (unsigned)sons.y;
             } else {
-                double cj[3], wj[3];
-                load_geom(a.geom, jm, cj, wj);
                 int pruned = 0;
                 if (remote) {
                     if (!lj) pruned = pruned_dev(cj, wj, pc.shift[img], a.tc, a.tw, a.cutoff, a.theta, a.longshort);
@@ -240,7 +242,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NODE_MIN_BLOCKS) frontier_nod
                     if (open_i) { no = 1; o0 = jme; }
                     else {
                         npush = 2;
-                        p0 = (unsigned)a.son[2 * (size_t)jm] | imgbits; p1 = (unsigned)a.son[2 * (size_t)jm + 1] | imgbits;
+                        p0 = (unsigned)sons.x | imgbits; p1 = (unsigned)sons.y | imgbits;
                     }
                 }
             }

@@ -1,5 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-( timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 ) > gpurun_out/pytest_gpu.log
-tail -3 gpurun_out/pytest_gpu.log
-bash tools/sweep.sh "-DLEAF_MIN_BLOCKS=5;-DLEAF_MIN_BLOCKS=6;-DLEAF_MIN_BLOCKS=4;-DLEAF_MIN_BLOCKS=7" 256 2>&1 | tee gpurun_out/sweep_fused2.log
+python bench.py > gpurun_out/bench_512_r01h.json 2> gpurun_out/bench_512_r01h.err; tail -c 2500 gpurun_out/bench_512_r01h.json
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_r01h.json 2> gpurun_out/bench_ref_r01h.err; tail -c 600 gpurun_out/bench_ref_r01h.json
+timeout 900 bash tools/profile.sh r01h 256
