@@ -16,17 +16,13 @@ void pn2_set_error(const char *fmt, ...) {
 }
 extern "C" const char *pn2_last_error(void) { return g_err; }
 
-// g(u) = exp(-u^2) (1 + u^2 R(u)); coefficients of R from tools/fit_g.py (weighted minimax, float32-checked)
-static const float PN2_R8[9] = {9.998987644e-01f, -7.508830079e-01f, 4.927910981e-01f, -2.807554342e-01f,
-                                1.325016193e-01f, -4.790751029e-02f, 1.200598312e-02f, -1.810827398e-03f,
-                                1.218777145e-04f};
-
 void pn2_init_consts(pn2_ctx *h) {
     P2PConst &c = h->pc;
     memset(&c, 0, sizeof c);
     const pn2_params &p = h->prm;
     c.rs = p.rs; c.soft = p.soft; c.mass = p.mass;
     c.inv2rs = 1.0 / (2.0 * p.rs);
+    c.inv_len = 1.0 / (2.0 * p.rs * 0.83255461115769775635);
     c.longshort = p.longshort;
     // image displacements in the order of src/fmm.c:1028-1037 (mi, mj, mk in -1..1, (0,0,0) skipped)
     int k = 1;
@@ -37,8 +33,7 @@ void pn2_init_consts(pn2_ctx *h) {
                 c.shift[k][0] = a * p.box; c.shift[k][1] = b * p.box; c.shift[k][2] = d * p.box;
                 k++;
             }
-    for (int i = 0; i < 9; i++) c.q[i] = PN2_R8[i];
-    double ie = (p.soft > 0.0) ? 2.0 * p.rs / p.soft : 1e12;
+    double ie = (p.soft > 0.0) ? 1.0 / (c.inv_len * p.soft) : 1e12;
     if (ie > 1e12) ie = 1e12;
     c.inv_eps = (float)ie;
 }

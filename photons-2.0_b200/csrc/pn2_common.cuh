@@ -68,11 +68,11 @@ struct SourceSet {
 };
 
 struct P2PConst {
-    double inv2rs;            // 1 / (2 rs): FP32 positions are stored in units of 2 rs
+    double inv2rs;            // 1 / (2 rs): the argument of the split factor, u = r / 2 rs (FP64 mode)
+    double inv_len;           // 1 / lambda, lambda = 2 rs sqrt(ln 2): FP32 positions are stored in units of lambda (pn2_p2p.cuh)
     double rs, soft, mass;
     double shift[27][3];      // image displacements; index 0 = none, 1..26 = order of src/fmm.c:1028-1037
-    float q[12];              // g(u) = exp(-u^2) * sum q[k] u^k   (weighted minimax fit)
-    float inv_eps;            // 2 rs / soft
+    float inv_eps;            // lambda / soft
     int longshort;
 };
 

@@ -52,10 +52,10 @@ p2p_csr_f32_kernel(long nseg, const int *__restrict__ seg_sink, const long *__re
             LeafDesc d = src_desc[cell];
             if (j < d.npart) {
                 float4 r = src_rel[d.first + j];
-                // displacement of the source leaf centre from the sink leaf centre, in units of 2 rs
-                float Dx = (float)(((d.c[0] + pc.shift[img][0]) - sd.c[0]) * pc.inv2rs);
-                float Dy = (float)(((d.c[1] + pc.shift[img][1]) - sd.c[1]) * pc.inv2rs);
-                float Dz = (float)(((d.c[2] + pc.shift[img][2]) - sd.c[2]) * pc.inv2rs);
+                // displacement of the source leaf centre from the sink leaf centre, in units of lambda
+                float Dx = (float)(((d.c[0] + pc.shift[img][0]) - sd.c[0]) * pc.inv_len);
+                float Dy = (float)(((d.c[1] + pc.shift[img][1]) - sd.c[1]) * pc.inv_len);
+                float Dz = (float)(((d.c[2] + pc.shift[img][2]) - sd.c[2]) * pc.inv_len);
                 p = make_float4(r.x + Dx, r.y + Dy, r.z + Dz, 1.f);
             }
             if (j == 0) nint += (unsigned long long)(d.npart - ((local_src && e == (unsigned)sink) ? 1 : 0));
@@ -94,8 +94,8 @@ p2p_csr_f32_kernel(long nseg, const int *__restrict__ seg_sink, const long *__re
         nint += __shfl_xor_sync(0xffffffffu, nint, m);
     }
     if (q == 0 && j < sd.npart) {
-        // back to length units: positions were scaled by 1/(2 rs), so dx/r^3 carries (1/2rs)^2
-        const double sc = pc.mass * pc.inv2rs * pc.inv2rs;
+        // back to length units: positions were scaled by 1/lambda, so dx/r^3 carries (1/lambda)^2
+        const double sc = pc.mass * pc.inv_len * pc.inv_len;
         double *a = acc + 3 * (size_t)(sd.first + j);
         a[0] += (double)ax * sc; a[1] += (double)ay * sc; a[2] += (double)az * sc;
     }
@@ -156,22 +156,22 @@ p2p_csr_f64_kernel(long nseg, const int *__restrict__ seg_sink, const long *__re
 
 // leaf-centre-relative scaled coordinates: one thread per (leaf, slot)
 __global__ void relpos_kernel(int nleaf, const LeafDesc *__restrict__ desc, const double *__restrict__ pos,
-                              float4 *__restrict__ rel, double inv2rs, int maxleaf) {
+                              float4 *__restrict__ rel, double inv_len, int maxleaf) {
     long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
     int k = (int)(t / maxleaf), s = (int)(t % maxleaf);
     if (k >= nleaf) return;
     LeafDesc d = desc[k];
     if (s >= d.npart) return;
     const double *p = pos + 3 * (size_t)(d.first + s);
-    rel[d.first + s] = make_float4((float)((p[0] - d.c[0]) * inv2rs), (float)((p[1] - d.c[1]) * inv2rs),
-                                   (float)((p[2] - d.c[2]) * inv2rs), 1.f);
+    rel[d.first + s] = make_float4((float)((p[0] - d.c[0]) * inv_len), (float)((p[1] - d.c[1]) * inv_len),
+                                   (float)((p[2] - d.c[2]) * inv_len), 1.f);
 }
 
 int pn2_launch_relpos(pn2_ctx *h, const double *pos, const LeafDesc *desc, int nleaf, float4 *rel, int n) {
     (void)n;
     if (nleaf == 0) return PN2_OK;
     long nt = (long)nleaf * h->prm.maxleaf;
-    relpos_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, h->stream>>>(nleaf, desc, pos, rel, h->pc.inv2rs, h->prm.maxleaf);
+    relpos_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, h->stream>>>(nleaf, desc, pos, rel, h->pc.inv_len, h->prm.maxleaf);
     h->launches++;
     KERNEL_CHECK();
     return PN2_OK;

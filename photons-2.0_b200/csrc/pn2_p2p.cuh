@@ -12,9 +12,9 @@
 // every lane streams the SW particles of its slice's leaf with broadcast LDS.128.  Slices are reduced
 // with __shfl_xor at the end, so every sink is owned by one warp: no atomics, deterministic sums.
 //
-// FP32 mode: coordinates are leaf-centre-relative and in units of 2 rs (u = r directly):
-//     3 FADD (dx) + 3 FFMA (r^2) + MUFU.RSQ + FMUL (u) + FMUL + MUFU.EX2 (exp(-u^2)) + 9 FFMA (1 + u^2 R(u))
-//     + FMNMX (softening) + 2 FMUL (1/r^3) + 2 FMUL (e, Q) + 3 FFMA (accumulate)  = 24 FMA-pipe + 2 MUFU + 1 ALU
+// FP32 mode: coordinates are leaf-centre-relative and in units of lambda = 2 rs sqrt(ln 2) (see below):
+//     3 FADD (dx) + 3 FFMA (r^2) + MUFU.RSQ + FMUL (u) + MUFU.EX2 (2^(-r^2)) + 9 FFMA (1 + u^2 R(u))
+//     + FMNMX (softening) + 2 FMUL (1/r^3) + 2 FMUL (e, Q) + 3 FFMA (accumulate)  = 23 FMA-pipe + 2 MUFU + 1 ALU
 #pragma once
 #include "pn2_common.cuh"
 
@@ -32,6 +32,18 @@
 #else
 #error "PN2_RDEG must be 6 or 8"
 #endif
+// FP32 length unit: lambda = 2 rs sqrt(ln 2), so that exp(-u^2) = 2^(-r'^2) with r' = r / lambda and MUFU.EX2 takes
+// -r'^2 directly (saves the multiplication by log2 e per interaction).  The polynomial is rescaled accordingly at
+// compile time: 1 + u^2 R(u) = 1 + r'^2 R'(r'),  R'_k = R_k (sqrt(ln 2))^(k+2).
+#define PN2_SQRT_LN2 0.83255461115769775635
+struct Pn2RCoef {
+    float v[PN2_RDEG + 1];
+    constexpr Pn2RCoef() : v{} {
+        constexpr double c[PN2_RDEG + 1] = PN2_RCOEF;
+        double f = PN2_SQRT_LN2 * PN2_SQRT_LN2;
+        for (int k = 0; k <= PN2_RDEG; k++) { v[k] = (float)(c[k] * f); f *= PN2_SQRT_LN2; }
+    }
+};
 #define PN2_PAD_COORD 24.0f      // padding sources sit at u >= 24: exp(-u^2) underflows to exactly 0
 
 #ifndef PN2_PACKED
@@ -88,7 +100,7 @@ __device__ __forceinline__ float pn2_rsqrt(float x) {   // bare MUFU.RSQ
 template <bool LONGSHORT>
 __device__ __forceinline__ void p2p_interact_f32(const float4 pj, float xi, float yi, float zi, float &ax, float &ay,
                                                  float &az, float inv_eps) {
-    constexpr float q[PN2_RDEG + 1] = PN2_RCOEF;
+    constexpr Pn2RCoef qq{};
     float dx = pj.x - xi, dy = pj.y - yi, dz = pj.z - zi;
     float r2 = fmaf(dx, dx, 1e-30f);
     r2 = fmaf(dy, dy, r2);
@@ -98,10 +110,10 @@ __device__ __forceinline__ void p2p_interact_f32(const float4 pj, float xi, floa
     float s = ri * ri * ri;
     if (LONGSHORT) {
         float u = r2 * rinv;
-        float e = pn2_ex2(r2 * -1.4426950408889634f);
-        float Q = q[PN2_RDEG];
+        float e = pn2_ex2(-r2);
+        float Q = qq.v[PN2_RDEG];
 #pragma unroll
-        for (int k = PN2_RDEG - 1; k >= 0; k--) Q = fmaf(Q, u, q[k]);
+        for (int k = PN2_RDEG - 1; k >= 0; k--) Q = fmaf(Q, u, qq.v[k]);
         Q = fmaf(Q, r2, 1.0f);
         s = s * e * Q;
     } else {
@@ -113,8 +125,8 @@ __device__ __forceinline__ void p2p_interact_f32(const float4 pj, float xi, floa
 }
 
 // Packed form: one sink lane against TWO staged sources.  Same operations as p2p_interact_f32, each FMA-pipe
-// instruction doing both sources: 3 FADD2 + 3 FFMA2 + 2 FMUL2 (1/r^3) + FMUL2 (u) + FMUL2 (-u^2 log2 e) + 9 FFMA2
-// + 2 FMUL2 + 3 FFMA2 = 24 FMA-pipe instructions, 4 MUFU, 2 FMNMX, 2 LDS per PAIR of interactions (16 issue
+// instruction doing both sources: 3 FADD2 + 3 FFMA2 + 2 FMUL2 (1/r^3) + FMUL2 (u) + 9 FFMA2
+// + 2 FMUL2 + 3 FFMA2 = 23 FMA-pipe instructions, 4 MUFU, 2 FMNMX, 2 LDS per PAIR of interactions (16 issue
 // slots per interaction instead of 28), so the FMA pipe (2 cycles per FP32x2 instruction), not the issue port, bounds it.
 struct P2PSinkPk {
     pn2_f2 nx, ny, nz;      // (-xi, -xi) ...
@@ -122,7 +134,7 @@ struct P2PSinkPk {
 };
 template <bool LONGSHORT>
 __device__ __forceinline__ void p2p_interact_pk(const float *pair /* 8 floats, 16-byte aligned */, P2PSinkPk &sk, float inv_eps) {
-    constexpr float q[PN2_RDEG + 1] = PN2_RCOEF;
+    constexpr Pn2RCoef qq{};
     const ulonglong2 xy = *reinterpret_cast<const ulonglong2 *>(pair);
     pn2_f2 dx = add2(xy.x, sk.nx), dy = add2(xy.y, sk.ny);
     pn2_f2 zz, ww = 0;
@@ -139,13 +151,10 @@ __device__ __forceinline__ void p2p_interact_pk(const float *pair /* 8 floats, 1
     pn2_f2 s = mul2(mul2(ri, ri), ri);
     if (LONGSHORT) {
         const pn2_f2 u = mul2(r2, pk2(rinva, rinvb));
-        const pn2_f2 t = mul2(r2, pk2(-1.4426950408889634f, -1.4426950408889634f));
-        float ta, tb;
-        unpk2(t, ta, tb);
-        const pn2_f2 e = pk2(pn2_ex2(ta), pn2_ex2(tb));
-        pn2_f2 Q = pk2(q[PN2_RDEG], q[PN2_RDEG]);
+        const pn2_f2 e = pk2(pn2_ex2(-r2a), pn2_ex2(-r2b));
+        pn2_f2 Q = pk2(qq.v[PN2_RDEG], qq.v[PN2_RDEG]);
 #pragma unroll
-        for (int k = PN2_RDEG - 1; k >= 0; k--) Q = fma2(Q, u, pk2(q[k], q[k]));
+        for (int k = PN2_RDEG - 1; k >= 0; k--) Q = fma2(Q, u, pk2(qq.v[k], qq.v[k]));
         Q = fma2(Q, r2, pk2(1.0f, 1.0f));
         s = mul2(mul2(s, e), Q);
     } else {

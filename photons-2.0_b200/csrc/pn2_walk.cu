@@ -22,7 +22,9 @@
 // pruning of prepare_sendtree2 (src/remotes.c:97-158) is evaluated on the fly for the visited node.
 #include "pn2_p2p.cuh"
 
+#ifndef WALK_WARPS
 #define WALK_WARPS 4
+#endif
 #define STACK_CAP 512
 #define SRCQ_CAP 64
 #define OBUF_CAP 256              // per-warp staging of O(im) before it is flushed to a span
@@ -61,27 +63,30 @@ struct WalkArgs {
     int nwork;
 };
 
-// acceptance(), src/fmm.c:267-326: 0 open, 1 accept, -1 drop
+// acceptance(), src/fmm.c:267-326: 0 open, 1 accept, -1 drop.  Same expressions in the same order (this file is
+// compiled with -fmad=false); the reference's early returns are written as selects applied in reverse priority,
+// which gives the same result without divergent branches.
 __device__ __forceinline__ int accept_dev(const double *wi, const double *wj, double dx, double dy, double dz,
                                           double cutoff, double theta, int longshort) {
-    double w0 = (wi[0] + wj[0]) * 0.5, w1 = (wi[1] + wj[1]) * 0.5, w2 = (wi[2] + wj[2]) * 0.5;
-    double dd2 = dx * dx + dy * dy + dz * dz;
+    const double w0 = (wi[0] + wj[0]) * 0.5, w1 = (wi[1] + wj[1]) * 0.5, w2 = (wi[2] + wj[2]) * 0.5;
+    const double dd2 = dx * dx + dy * dy + dz * dz;
     double g0 = fabs(dx) - w0, g1 = fabs(dy) - w1, g2 = fabs(dz) - w2;
-    if (g0 <= 0.0) g0 = 0.0;
-    if (g1 <= 0.0) g1 = 0.0;
-    if (g2 <= 0.0) g2 = 0.0;
-    if (g0 + g1 + g2 < 0.0001) return 0;
-    double dm2 = g0 * g0 + g1 * g1 + g2 * g2;
-    if (longshort) {
-        double c2 = cutoff * cutoff;
-        if (dm2 >= c2) return -1;
-        if (dd2 > 1.0 * c2) return 0;
-    }
+    g0 = g0 <= 0.0 ? 0.0 : g0;
+    g1 = g1 <= 0.0 ? 0.0 : g1;
+    g2 = g2 <= 0.0 ? 0.0 : g2;
+    const double dm2 = g0 * g0 + g1 * g1 + g2 * g2;
     double wmax = w0;
-    if (w1 > wmax) wmax = w1;
-    if (w2 > wmax) wmax = w2;
+    wmax = w1 > wmax ? w1 : wmax;
+    wmax = w2 > wmax ? w2 : wmax;
     wmax *= 2;
-    return (wmax * wmax < theta * theta * dd2) ? 1 : 0;
+    int f = (wmax * wmax < theta * theta * dd2) ? 1 : 0;
+    if (longshort) {
+        const double c2 = cutoff * cutoff;
+        f = (dd2 > 1.0 * c2) ? 0 : f;
+        f = (dm2 >= c2) ? -1 : f;
+    }
+    f = (g0 + g1 + g2 < 0.0001) ? 0 : f;
+    return f;
 }
 
 // prepare_sendtree2's pruning test for a node displaced by sh (src/remotes.c:97-158): 1 = terminal
@@ -284,7 +289,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NODE_MIN_BLOCKS) frontier_nod
 // LeafWalk resolves the frontier of ONE sink leaf, 32 stack entries per step, and appends the source leaves it
 // finds to a per-warp queue of 16-byte entries:
 //     FP32 mode (MODE 0): {tile, dx, dy, dz}  tile = leaf tile index, d = source leaf centre - sink leaf centre
-//                                             (+ image shift) in units of 2 rs
+//                                             (+ image shift) in units of lambda = 2 rs sqrt(ln 2)
 //     FP64 / dump modes : {first, npart, cell | image << 26, 0}
 template <int MODE, int U, int QCAP>     // U = stack entries per lane and step (32 U per step): the walk is latency-bound,
 struct LeafWalk {                        // wider steps mean fewer dependent round trips per leaf; QCAP = queue capacity
@@ -359,9 +364,9 @@ struct LeafWalk {                        // wider steps mean fewer dependent rou
                     const int dfirst = __double2loint(r1[u].y), dnpart = __double2hiint(r1[u].y);
                     if (MODE == 0) {
                         ent.x = jm < a.nleaf ? jm : jm - a.rleaf0 + a.nleaf;
-                        ent.y = __float_as_int((float)(((r0[u].x + pc.shift[img][0]) - sd.c[0]) * pc.inv2rs));
-                        ent.z = __float_as_int((float)(((r0[u].y + pc.shift[img][1]) - sd.c[1]) * pc.inv2rs));
-                        ent.w = __float_as_int((float)(((r1[u].x + pc.shift[img][2]) - sd.c[2]) * pc.inv2rs));
+                        ent.y = __float_as_int((float)(((r0[u].x + pc.shift[img][0]) - sd.c[0]) * pc.inv_len));
+                        ent.z = __float_as_int((float)(((r0[u].y + pc.shift[img][1]) - sd.c[1]) * pc.inv_len));
+                        ent.w = __float_as_int((float)(((r1[u].x + pc.shift[img][2]) - sd.c[2]) * pc.inv_len));
                     } else {
                         ent = make_int4(dfirst, dnpart, (int)jme[u], 0);
                     }
@@ -469,17 +474,20 @@ __global__ void __launch_bounds__(WALK_WARPS * 32) walk_leaf_kernel(WalkArgs a, 
 // FP32 product kernel: one warp per sink leaf, list walk fused with the P2P evaluation
 // ------------------------------------------------------------------------------------------------
 // Sources are read as LEAF TILES: every leaf owns one tile of SW slots in HBM, already in the packed-pair layout of
-// the P2P loop (pn2_p2p.cuh: SW/2 pairs of {x0 x1 y0 y1 | z0 z1 w0 w1}, leaf-centre-relative, units of 2 rs, unused
+// the P2P loop (pn2_p2p.cuh: SW/2 pairs of {x0 x1 y0 y1 | z0 z1 w0 w1}, leaf-centre-relative, units of lambda = 2 rs sqrt(ln 2), unused
 // slots = far-away zero-weight padding), so staging a source leaf is a plain 16 * SW byte copy: the warp issues
 // cp.async (LDGSTS.128: no registers, no arithmetic) for a whole BATCH of queued leaves at once and goes on walking
 // while the copies land; the per-leaf centre offset is applied on the SINK side (3 FADD per lane and stage).
 // (A warp-specialised persistent variant -- walker warps feeding P2P warps through an mbarrier ring, setmaxnreg --
 // was built and measured slower, 61.5 vs 48.1 ms at 256^3: one latency-bound walker cannot feed one P2P warp, see
 // DESIGN.md 4.3.)
+#ifndef FUSED_NST
+#define FUSED_NST 8
+#endif
 template <int SW>
 struct FusedLayout {
     static constexpr int NSL = 32 / SW;
-    static constexpr int NST = 8;                         // stages per batch
+    static constexpr int NST = FUSED_NST;                 // stages per batch
     static constexpr int BATCH = NST * NSL;               // source leaves per batch (32 / 16 / 8)
     static constexpr int TB = 16 * SW;                    // tile bytes
     static constexpr int ROWB = TB + 16;                  // row stride: the 16 spare bytes hold the leaf's {tile, dx, dy, dz}
@@ -585,7 +593,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, LEAF_MIN_BLOCKS) walk_fused_k
     }
     const LeafDesc sd = w.sd;
     if (q == 0 && j < sd.npart) {
-        const double sc = pc.mass * pc.inv2rs * pc.inv2rs;
+        const double sc = pc.mass * pc.inv_len * pc.inv_len;
         double *o = a.acc + 3 * (size_t)(sd.first + j);
         o[0] += (double)ax * sc; o[1] += (double)ay * sc; o[2] += (double)az * sc;
     }

@@ -1,5 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python bench.py > gpurun_out/bench_512_r01h.json 2> gpurun_out/bench_512_r01h.err; tail -c 2500 gpurun_out/bench_512_r01h.json
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_r01h.json 2> gpurun_out/bench_ref_r01h.err; tail -c 600 gpurun_out/bench_ref_r01h.json
-timeout 900 bash tools/profile.sh r01h 256
+( timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 ) > gpurun_out/pytest_gpu.log
+tail -3 gpurun_out/pytest_gpu.log
+./tools/ubench/ubench_p2p 2>&1 | tail -7
+bash tools/sweep.sh "-DFUSED_NST=8;-DFUSED_NST=4;-DFUSED_NST=16 -DLEAF_MIN_BLOCKS=4;-DWALK_WARPS=2 -DLEAF_MIN_BLOCKS=10;-DWALK_WARPS=8 -DLEAF_MIN_BLOCKS=2;-DFUSED_NST=4 -DLEAF_MIN_BLOCKS=6" 256 2>&1 | tee gpurun_out/sweep_nst.log

@@ -129,8 +129,6 @@ int main() {
     ms = timeit(lp<4>, 5); printf("MUFU only              : %.2f Tmufu/s = %.2f per clk per SM\n", thr * g_iters * 16 / ms / 1e9, thr * g_iters * 16 / ms / 1e-3 / (sms * clk * 1e3));
     // P2P inner loop
     memset(&g_pc, 0, sizeof g_pc);
-    const float qf[9] = {0.f, 0.f, 0.7522527f, -0.0004f, -0.4496f, -0.012f, 0.19f, -0.08f, 0.011f};
-    for (int k = 0; k < 9; k++) g_pc.q[k] = qf[k];
     g_pc.inv_eps = 40.f; g_pc.longshort = 1;
     auto report = [&](const char *name, float ms_, int blocks) {
         double inter = (double)sms * blocks * 128 * g_stages * 8;
