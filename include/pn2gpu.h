@@ -166,6 +166,32 @@ int pn2_step_begin(pn2_ctx *h, const double *d_pos, int n, const pn2_domain *dom
 int pn2_exchange_local(pn2_ctx **hs, int nranks);
 int pn2_step_finish(pn2_ctx *h, double *d_acc);
 
+/* ---- domain decomposition on the device (src/domains.c:268-375) ------------------------------------------------
+ * Particles are RECORDS of rec_doubles doubles whose first three are the position (rec_doubles = 12 is the
+ * reference's Body, inc/typesdef.h:25-31: pos, acc, vel, acc_pm; 3 = bare positions).  `split` is the heap-numbered
+ * domain tree of inc/photoNs.h:285-291 / src/domains.c:399-428 as 2*nranks-1 doubles (host memory; only the
+ * nranks-1 internal nodes are read): node n has sons 2n+1, 2n+2, the direction cycles x, y, z from the root, a
+ * position with pos[D] > split goes right (bksort_body_inplace, src/domains.c:163-266), and domain node d belongs
+ * to rank (d - mostleft + nranks) % nranks (prepare_body_inOrderOf_domain, src/domains.c:268-296).
+ *
+ * pn2_domain_owner_device : the owner rank of every record (no data movement).
+ * pn2_migrate_begin       : classifies and orders the records by destination rank; sendcount[nranks] on return.
+ * pn2_migrate_exchange_nccl / pn2_migrate_exchange_local : the all-to-all-v of prepare_deliver_realloc_body
+ *     (src/domains.c:298-375) with grouped ncclSend/ncclRecv over the communicator of pn2_set_comm, or with
+ *     device-to-device copies between the contexts of one process.
+ * pn2_migrate_result      : the received records (device pointer owned by the context, valid until the next
+ *     pn2_migrate_begin) in the reference's order: blocks by source rank, ascending.
+ * pn2_migrate_fetch       : copies the received records to host memory (n_out * rec_doubles doubles), for a host
+ *     that keeps its Body array in host memory like the reference (part = part_b, src/domains.c:362-363).
+ * pn2_migrate_device      : begin + exchange_nccl + result (one rank: a local reorder). */
+int pn2_domain_owner_device(pn2_ctx *h, const double *d_rec, int rec_doubles, int n, const double *split, int nranks, int *d_owner);
+int pn2_migrate_begin(pn2_ctx *h, const double *d_rec, int rec_doubles, int n, const double *split, int *sendcount);
+int pn2_migrate_exchange_nccl(pn2_ctx *h);
+int pn2_migrate_exchange_local(pn2_ctx **hs, int nranks);
+int pn2_migrate_result(pn2_ctx *h, double **d_rec_out, int *n_out, int *recvcount);
+int pn2_migrate_fetch(pn2_ctx *h, double *rec_host_out);
+int pn2_migrate_device(pn2_ctx *h, const double *d_rec, int rec_doubles, int n, const double *split, double **d_rec_out, int *n_out);
+
 /* ---- Mode B inspection (tests: bit-exact tree / list checks; not needed by the product path) --- */
 typedef struct {
     int32_t n, nleaf, nnode, nlevel;

@@ -154,6 +154,7 @@ struct pn2_ctx {
     int rank = 0, nranks = 1;
     bool own_comm = false;
     struct LetState *let = nullptr;
+    struct MigState *mig = nullptr;     // domain decomposition (pn2_migrate.cu)
     std::vector<pn2_domain> all_dom;
     void *nccl = nullptr;
     cudaEvent_t ev[10] = {nullptr};
@@ -179,6 +180,7 @@ int pn2_let_pack_all(pn2_ctx *h);
 int pn2_let_exchange_nccl(pn2_ctx *h);
 int pn2_let_unpack(pn2_ctx *h);
 void pn2_let_release(pn2_ctx *h);
+void pn2_migrate_release(pn2_ctx *h);
 void pn2_comm_release(pn2_ctx *h);
 int pn2_step_begin(pn2_ctx *h, const double *d_pos, int n, const pn2_domain *dom);
 int pn2_step_finish(pn2_ctx *h, double *d_acc);

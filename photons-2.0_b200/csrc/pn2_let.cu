@@ -16,26 +16,10 @@
 // or device-to-device copies between contexts of one process (pn2_exchange_local; also what the
 // single-GPU tests use to drive two ranks).
 #include <cub/cub.cuh>
-#include <nccl.h>
 #include <dlfcn.h>
-#include "pn2_common.cuh"
+#include "pn2_nccl.cuh"
 
-// NCCL is bound at first use with dlopen, not at link time: a process that also imports torch must end up with ONE
-// libnccl.so.2 (torch's bundled 2.28 needs symbols the system 2.27 lacks).  Order: the copy already mapped into the
-// process, $PN2_NCCL_LIB (pn2gpu.py points it at torch's bundled library), the system library.
-namespace {
-struct NcclApi {
-    ncclResult_t (*GetUniqueId)(ncclUniqueId *);
-    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
-    ncclResult_t (*CommDestroy)(ncclComm_t);
-    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
-    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
-    ncclResult_t (*GroupStart)();
-    ncclResult_t (*GroupEnd)();
-    const char *(*GetErrorString)(ncclResult_t);
-    bool ok = false;
-};
-NcclApi g_nccl;
+Pn2NcclApi g_nccl;
 bool nccl_load() {
     if (g_nccl.ok) return true;
     void *hd = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
@@ -51,15 +35,6 @@ bool nccl_load() {
     g_nccl.ok = true;
     return true;
 }
-}  // namespace
-#define ncclGetUniqueId g_nccl.GetUniqueId
-#define ncclCommInitRank g_nccl.CommInitRank
-#define ncclCommDestroy g_nccl.CommDestroy
-#define ncclSend g_nccl.Send
-#define ncclRecv g_nccl.Recv
-#define ncclGroupStart g_nccl.GroupStart
-#define ncclGroupEnd g_nccl.GroupEnd
-#define ncclGetErrorString g_nccl.GetErrorString
 
 struct __align__(16) PackCell {
     double geom[6];
@@ -81,15 +56,6 @@ struct LetState {
     std::vector<long> s_nl, s_nn, s_np, r_nl, r_nn, r_np;   // per peer counts
     int psize = 16;
 };
-
-#define NCCL_TRY(expr)                                                                           \
-    do {                                                                                         \
-        ncclResult_t r_ = (expr);                                                                \
-        if (r_ != ncclSuccess) {                                                                 \
-            pn2_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, ncclGetErrorString(r_)); \
-            return PN2_ERR_NCCL;                                                                 \
-        }                                                                                        \
-    } while (0)
 
 // same arithmetic as pruned_dev (pn2_walk.cu) / prepare_sendtree2 (src/remotes.c:97-158); this file is
 // compiled with -fmad=false as well

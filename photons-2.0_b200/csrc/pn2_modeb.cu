@@ -13,6 +13,7 @@ void pn2_modeb_release(pn2_ctx *h) {
     h->b_scal.release(); h->m2l_pairs.release(); h->spans.release(); h->o_head.release(); h->lst_off.release(); h->lst_src.release(); h->lst_sink.release();
     for (int i = 0; i < 10; i++) if (h->ev[i]) { cudaEventDestroy(h->ev[i]); h->ev[i] = nullptr; }
     pn2_let_release(h);
+    pn2_migrate_release(h);
     pn2_comm_release(h);
 }
 

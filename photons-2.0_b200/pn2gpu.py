@@ -32,7 +32,9 @@ EXPORTS = ["pn2_create", "pn2_destroy", "pn2_set_params", "pn2_sync", "pn2_last_
            "pn2_get_multipoles", "pn2_get_locals", "pn2_get_counters", "pn2_force_step", "pn2_force_step_device",
            "pn2_set_comm", "pn2_get_step_info", "pn2_get_order", "pn2_get_cells", "pn2_get_lists", "pn2_fma_peak",
            "pn2_get_timings", "pn2_launch_count", "pn2_timer_start", "pn2_timer_stop", "pn2_comm_unique_id",
-           "pn2_comm_init_rank", "pn2_step_begin", "pn2_exchange_local", "pn2_step_finish"]
+           "pn2_comm_init_rank", "pn2_step_begin", "pn2_exchange_local", "pn2_step_finish", "pn2_domain_owner_device",
+           "pn2_migrate_begin", "pn2_migrate_exchange_nccl", "pn2_migrate_exchange_local", "pn2_migrate_result",
+           "pn2_migrate_device", "pn2_migrate_fetch"]
 
 
 class Pn2Error(RuntimeError):
@@ -129,6 +131,13 @@ def lib():
     L.pn2_step_begin.argtypes = [vp, vp, C.c_int, C.POINTER(Domain)]
     L.pn2_exchange_local.argtypes = [C.POINTER(vp), C.c_int]
     L.pn2_step_finish.argtypes = [vp, vp]
+    L.pn2_domain_owner_device.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_int, vp]
+    L.pn2_migrate_begin.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp]
+    L.pn2_migrate_exchange_nccl.argtypes = [vp]
+    L.pn2_migrate_exchange_local.argtypes = [C.POINTER(vp), C.c_int]
+    L.pn2_migrate_result.argtypes = [vp, C.POINTER(vp), ip, vp]
+    L.pn2_migrate_device.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.POINTER(vp), ip]
+    L.pn2_migrate_fetch.argtypes = [vp, vp]
     L.pn2_timer_start.argtypes = [vp, C.c_int]
     L.pn2_timer_stop.argtypes = [vp, C.c_int, dp]
     L.pn2_launch_count.argtypes = [vp]
@@ -161,6 +170,7 @@ class Context:
     def __init__(self, params, device=0):
         self.h = C.c_void_p()
         self.params = params
+        self.nranks = 1
         _ck(lib().pn2_create(C.byref(self.h), device, C.byref(params)))
 
     def close(self):
@@ -263,6 +273,7 @@ class Context:
     def set_comm(self, rank, nranks, domains, nccl_comm):
         arr = (Domain * nranks)(*domains)
         _ck(lib().pn2_set_comm(self.h, rank, nranks, arr, nccl_comm))
+        self.nranks = nranks
 
     def set_comm_torch(self, rank, nranks, domains):
         """Create this context's own NCCL communicator; the 128-byte unique id travels over torch.distributed
@@ -278,6 +289,7 @@ class Context:
         idb = (C.c_ubyte * 128).from_buffer_copy(raw)
         arr = (Domain * nranks)(*domains)
         _ck(lib().pn2_comm_init_rank(self.h, rank, nranks, arr, idb))
+        self.nranks = nranks
 
     def step_begin(self, d_pos_ptr, n, domain):
         _ck(lib().pn2_step_begin(self.h, d_pos_ptr, n, C.byref(domain)))
@@ -305,6 +317,43 @@ class Context:
             domain = make_domain([0, 0, 0], [b, b, b], 0)
         _ck(lib().pn2_force_step_device(self.h, d_pos_ptr, n, C.byref(domain), d_acc_ptr))
         self.n = n
+
+    # ---- domain decomposition on the device (src/domains.c:268-375) ----
+    def domain_owner_device(self, d_rec_ptr, rec_doubles, n, splits, nranks, d_owner_ptr):
+        """Owner rank of n device records (first three doubles = position) under the domain-tree splits."""
+        sp = np.ascontiguousarray(splits, np.float64)
+        _ck(lib().pn2_domain_owner_device(self.h, d_rec_ptr, rec_doubles, n, sp.ctypes.data, nranks, d_owner_ptr))
+
+    def migrate_begin(self, d_rec_ptr, rec_doubles, n, splits):
+        """Classify and order the records by destination rank; returns sendcount[nranks]."""
+        sp = np.ascontiguousarray(splits, np.float64)
+        sc = np.zeros(max(1, self.nranks), np.int32)
+        _ck(lib().pn2_migrate_begin(self.h, d_rec_ptr, rec_doubles, n, sp.ctypes.data, sc.ctypes.data))
+        return sc
+
+    def migrate_exchange_nccl(self):
+        _ck(lib().pn2_migrate_exchange_nccl(self.h))
+
+    def migrate_result(self):
+        """(device pointer, n, recvcount[nranks]) of the records this rank owns after the exchange."""
+        ptr, n = C.c_void_p(), C.c_int()
+        rc = np.zeros(max(1, self.nranks), np.int32)
+        _ck(lib().pn2_migrate_result(self.h, C.byref(ptr), C.byref(n), rc.ctypes.data))
+        return ptr.value or 0, n.value, rc
+
+    def migrate_fetch(self, rec_doubles):
+        """The received records as a host array (n, rec_doubles)."""
+        _, n, _ = self.migrate_result()
+        out = np.zeros((n, rec_doubles))
+        _ck(lib().pn2_migrate_fetch(self.h, out.ctypes.data))
+        return out
+
+    def migrate_device(self, d_rec_ptr, rec_doubles, n, splits):
+        """prepare_deliver_realloc_body (src/domains.c:298-375) over NCCL: returns (device pointer, n_new)."""
+        self.migrate_begin(d_rec_ptr, rec_doubles, n, splits)
+        self.migrate_exchange_nccl()
+        ptr, n_new, _ = self.migrate_result()
+        return ptr, n_new
 
     def step_info(self):
         s = StepInfo()
@@ -374,6 +423,12 @@ def short_range_force_mode_a(ctx, part_pos, leaf, first_leaf, btree, first_node,
         ctx.m2l_ext_batch(*rm2l)
     ctx.l2l_l2p()
     return ctx.get_acc()
+
+
+def migrate_exchange_local(ctxs):
+    """The all-to-all-v of the records between contexts of this process (after migrate_begin on every rank)."""
+    arr = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+    _ck(lib().pn2_migrate_exchange_local(arr, len(ctxs)))
 
 
 def exchange_local(ctxs):

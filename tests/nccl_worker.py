@@ -48,6 +48,33 @@ def main():
             assert err < tol, err
         worst = max(worst, err)
         ctx.close()
+    # ---- domain decomposition over NCCL (pn2_migrate_*, src/domains.c:268-375) against the reference's golden owners ----
+    gd = np.load(os.path.join(ROOT, "tests", "golden", "domains_golden.npz"))
+    case = {2: 0, 4: 2, 8: 4}.get(world)
+    if case is not None:
+        sub = pos[::int(gd["pos_stride"])]
+        n = len(sub)
+        splits, own = gd[f"splits{case}"][0], gd[f"owner{case}"][0]
+        rec = np.zeros((n, 12))
+        rec[:, :3] = sub
+        rec[:, 6] = np.arange(n)
+        prm = pn2gpu.make_params(box, 32, len(pos), float(g["mass"]))
+        ctx = pn2gpu.Context(prm, device=local)
+        ctx.set_comm_torch(rank, world, doms)
+        held = torch.from_numpy(rec[rank::world].copy()).cuda()
+        for _ in range(2):
+            ptr, m = ctx.migrate_device(held.data_ptr(), 12, held.shape[0], splits)
+            out = ctx.migrate_fetch(12)
+        tags = out[:, 6].astype(np.int64)
+        assert m == int((own == rank).sum()), (m, int((own == rank).sum()))
+        assert np.array_equal(np.sort(tags), np.flatnonzero(own == rank))
+        assert np.array_equal(out, rec[tags])
+        cnt = torch.tensor([m], device="cuda")
+        dist.all_reduce(cnt)
+        assert int(cnt) == n
+        if rank == 0:
+            print(f"NCCL NP={world} migration: {n} records of 96 bytes, every rank holds the reference's set", flush=True)
+        ctx.close()
     dist.destroy_process_group()
     if rank == 0:
         print("NCCL_WORKER_OK", flush=True)

@@ -67,3 +67,26 @@ print("ok", rank)
                        env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("ok") == 2
+
+
+def test_adaptive_splits_match_reference_golden():
+    """DomainTree.update (measure_domain_runtime + determine_split_domtree, src/domains.c:21-38, 86-160) and the owner
+    rule under the adjusted splits, against the unmodified reference (tests/golden/make_domain_golden.py)."""
+    import domains
+    g = np.load(os.path.join(ROOT, "tests", "golden", "domains_golden.npz"))
+    pos = np.load(os.path.join(ROOT, "tests", "golden", "demo_pos_f32.npy")).astype(np.float64)[::int(g["pos_stride"])]
+    for ci in range(int(g["ncase"])):
+        P = int(g[f"P{ci}"])
+        dt = domains.DomainTree(P, float(g["box"]))
+        np.testing.assert_array_equal(dt.splits[:P - 1], g[f"split0_{ci}"][:P - 1])
+        for k, load in enumerate(g[f"loads{ci}"]):
+            dt.update(load)
+            np.testing.assert_array_equal(dt.splits[:P - 1], g[f"splits{ci}"][k][:P - 1])       # bit-exact doubles
+            own = dt.owner(pos)
+            np.testing.assert_array_equal(own, g[f"owner{ci}"][k])
+            np.testing.assert_array_equal(np.bincount(own, minlength=P), g[f"sendcount{ci}"][k])
+            # every rank's particles lie inside its box
+            doms = dt.boxes()
+            for r in range(P):
+                q = pos[own == r]
+                assert np.all(q >= np.array(doms[r].lo)) and np.all(q <= np.array(doms[r].hi))

@@ -1,0 +1,81 @@
+"""Size-independent properties of the Mode B force step at sizes the CPU oracle cannot reach in seconds
+(synthetic LCDM-like 128^3 = 2.1e6 particles, the bench generator; the same checks hold at 512^3, where
+bench.py reports `check_rms_acc`):
+
+  * FP32 mode against FP64 mode on the same device-built tree: rms rel err <= 1e-4 (north_star's FP32 tolerance;
+    FP64 mode itself is pinned to the unmodified reference at small sizes in test_gpu_mode_b.py);
+  * the two modes build the same tree and the same lists (interaction counts, M2L pairs, walk visits equal);
+  * tree invariants: the order is a permutation, leaves tile the particle range, every particle lies inside
+    its leaf's box (split-cell boxes, src/fmm.c:140-156), a node's range is the union of its sons';
+  * Newton's third law: with NSIDE = NPARTSIDE the step is P2P only and the lists are symmetric, so the total
+    momentum change vanishes to rounding;
+  * idempotence: a second step on the same positions returns bit-identical accelerations (no atomics in the sums).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+SIDE = 128
+
+
+@pytest.fixture(scope="module")
+def workload():
+    import torch
+    import synthetic
+    pos = synthetic.lcdm_like(SIDE, disp_rms=0.3, seed=12345, device="cuda").cpu().numpy()
+    return pos, synthetic.BOX, synthetic.particle_mass(SIDE ** 3)
+
+
+def run(pn2, pos, box, mass, precision):
+    prm = pn2.make_params(box, SIDE, SIDE ** 3, mass, maxleaf=8, theta=0.4, precision=precision)
+    ctx = pn2.Context(prm)
+    acc = ctx.force_step(pos)
+    return ctx, acc
+
+
+def test_fp32_vs_fp64_and_invariants(pn2, workload):
+    pos, box, mass = workload
+    n = pos.shape[0]
+    c64, a64 = run(pn2, pos, box, mass, pn2.FP64)
+    c32, a32 = run(pn2, pos, box, mass, pn2.FP32)
+    i64, i32 = c64.step_info(), c32.step_info()
+    for k in ("nleaf", "nnode", "nlevel", "n_interactions", "n_m2l_pairs", "n_p2p_pairs", "n_walk_visits"):
+        assert i64[k] == i32[k], k
+    assert 2400 < i64["n_interactions"] / n < 2900            # 2.5-2.7 k interactions per particle
+    err = np.sqrt(((a32 - a64) ** 2).sum() / (a64 ** 2).sum())
+    print(f"{SIDE}^3: FP32 mode vs FP64 mode rms rel err {err:.3e}; {i64['n_interactions'] / n:.1f} interactions/particle")
+    assert err <= 1e-4
+
+    # momentum balance (uniform mass): |sum a| against sum |a|
+    for a, tol in ((a64, 1e-6), (a32, 1e-5)):
+        assert np.abs(a.sum(axis=0)).max() <= tol * np.abs(a).sum()
+
+    # tree invariants
+    order = c64.get_order()
+    assert np.array_equal(np.sort(order), np.arange(n, dtype=order.dtype))
+    cells = c64.get_cells(with_ml=False)
+    nl = cells["nleaf"]
+    first, cnt = cells["range"][:nl, 0].astype(np.int64), cells["range"][:nl, 1].astype(np.int64)
+    o = np.argsort(first, kind="stable")
+    assert first[o][0] == 0 and np.array_equal(first[o][1:], (first[o] + cnt[o])[:-1]) and (first[o] + cnt[o])[-1] == n
+    assert cnt.max() <= 8
+    # every particle of the first 2000 leaves inside its leaf's box
+    p = pos[order]
+    for lf in range(0, 2000, 37):
+        c, w = cells["geom"][lf, :3], cells["geom"][lf, 3:]
+        q = p[first[lf]:first[lf] + cnt[lf]]
+        assert np.all(q >= c - 0.5 * w - 1e-9) and np.all(q <= c + 0.5 * w + 1e-9)
+    # nodes: range = union of the sons' ranges
+    son = cells["son"][nl:]
+    rng = cells["range"]
+    k = np.arange(0, son.shape[0], 97)
+    s0, s1 = son[k, 0], son[k, 1]
+    assert np.array_equal(rng[nl + k, 1], rng[s0, 1] + rng[s1, 1])
+    assert np.array_equal(rng[nl + k, 0], np.minimum(rng[s0, 0], rng[s1, 0]))
+
+
+def test_idempotent(pn2, workload):
+    pos, box, mass = workload
+    ctx, a1 = run(pn2, pos, box, mass, pn2.FP32)
+    a2 = ctx.force_step(pos)
+    assert np.array_equal(a1, a2)
