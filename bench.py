@@ -212,14 +212,40 @@ def main():
 
     # ---- workload: every rank generates the same field, keeps the particles of its own domain ----
     pos_all = synthetic.lcdm_like(args.npart_side, disp_rms=args.disp_rms, seed=12345, device=dev)
+    migrate = None
     if world > 1:
+        # every rank starts with an arbitrary slice of the set; the particles reach the rank that owns them under the
+        # reference's domain tree through the device migration (pn2_migrate_*: owner rule + all-to-all-v over NCCL)
         import domains
-        doms = domains.domain_boxes(world, synthetic.BOX)
-        owner = domains.domain_of(pos_all, world, synthetic.BOX)
-        pos = pos_all[owner == rank].contiguous()
-        del owner
+        dtree = domains.DomainTree(world, synthetic.BOX)
+        doms = dtree.boxes()
         dom = doms[rank]
         ctx.set_comm_torch(rank, world, doms)
+        held = pos_all[rank::world].contiguous()
+        n_own = int((domains.owner_of(pos_all, world, dtree.splits) == rank).sum())
+        del pos_all
+        torch.cuda.empty_cache()
+        torch.cuda.synchronize()
+        dist.barrier()
+        for it in range(2):                    # the first pass allocates the pools and opens the NCCL channels
+            ctx.sync()
+            dist.barrier()
+            ctx.timer_start(2)
+            ctx.migrate_begin(held.data_ptr(), 3, held.shape[0], dtree.splits)
+            ctx.migrate_exchange_nccl()
+            mig_ms = ctx.timer_stop(2)
+        _, n_new, _ = ctx.migrate_result()
+        if n_new != n_own:
+            raise SystemExit(f"bench.py: rank {rank} received {n_new} particles, owns {n_own}")
+        pos = torch.empty((n_new, 3), dtype=torch.float64, device=dev)
+        pn2gpu._ck(pn2gpu.lib().pn2_migrate_fetch(ctx.h, pos.data_ptr()))
+        tm = torch.tensor([mig_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        migrate = {"ms": float(tm[0]), "records": ntot, "record_bytes": 24,
+                   "gbytes_per_s": ntot * 24 / (float(tm[0]) * 1e-3) / 1e9,
+                   "what": "pn2_migrate_begin + pn2_migrate_exchange_nccl of all particles from a round-robin start (setup, not in the timed step)"}
+        del held
+        pos_all = None
     else:
         pos = pos_all
         dom = pn2gpu.make_domain([0, 0, 0], [synthetic.BOX] * 3, 0)
@@ -323,6 +349,7 @@ def main():
            "config": workload_config(args, world),
            "p2p_ginteractions_per_s": nint_total / (ms_step * 1e-3) / 1e9,
            "interactions_per_particle": nint_total / n_total,
+           "migrate": migrate,
            "phases_ms": {k: float(np.mean([p[k] for p in phase])) for k in ("tree", "upward", "frontier", "walk_p2p", "m2l", "downward", "let", "total")},
            "tree": {"nleaf": info["nleaf"], "nnode": info["nnode"], "levels": info["nlevel"], "m2l_pairs": info["n_m2l_pairs"],
                     "p2p_leaf_pairs": info["n_p2p_pairs"], "walk_visits": info["n_walk_visits"],

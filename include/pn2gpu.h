@@ -181,8 +181,9 @@ int pn2_step_finish(pn2_ctx *h, double *d_acc);
  *     device-to-device copies between the contexts of one process.
  * pn2_migrate_result      : the received records (device pointer owned by the context, valid until the next
  *     pn2_migrate_begin) in the reference's order: blocks by source rank, ascending.
- * pn2_migrate_fetch       : copies the received records to host memory (n_out * rec_doubles doubles), for a host
- *     that keeps its Body array in host memory like the reference (part = part_b, src/domains.c:362-363).
+ * pn2_migrate_fetch       : copies the received records to caller memory, host or device (n_out * rec_doubles
+ *     doubles), e.g. for a host that keeps its Body array in host memory like the reference (part = part_b,
+ *     src/domains.c:362-363).
  * pn2_migrate_device      : begin + exchange_nccl + result (one rank: a local reorder). */
 int pn2_domain_owner_device(pn2_ctx *h, const double *d_rec, int rec_doubles, int n, const double *split, int nranks, int *d_owner);
 int pn2_migrate_begin(pn2_ctx *h, const double *d_rec, int rec_doubles, int n, const double *split, int *sendcount);

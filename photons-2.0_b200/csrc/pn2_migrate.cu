@@ -251,7 +251,7 @@ extern "C" int pn2_migrate_fetch(pn2_ctx *h, double *rec_host_out) {
     if (M->n_recv > 0 && !rec_host_out) { pn2_set_error("pn2_migrate_fetch: bad argument"); return PN2_ERR_ARG; }
     CUDA_TRY(cudaSetDevice(h->device));
     if (M->n_recv > 0)
-        CUDA_TRY(cudaMemcpyAsync(rec_host_out, M->recv.p, (size_t)M->n_recv * M->rec * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaMemcpyAsync(rec_host_out, M->recv.p, (size_t)M->n_recv * M->rec * sizeof(double), cudaMemcpyDefault, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return PN2_OK;
 }
