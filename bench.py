@@ -358,7 +358,7 @@ def main():
                         "peak": fma_peak / 1e12, "unit": "Tops/s (FFMA/FMUL/FADD issue slots)", "frac": ach / fma_peak,
                         "peak_source": "measured in this run: pn2_fma_peak (independent FFMA chains, CUDA events)",
                         "nominal_peak_at_sampled_clock": (nominal / 1e12) if nominal else None,
-                        "ops_per_interaction": OPS_PER_INTERACTION, "traffic": traffic,
+                        "ops_per_interaction": OPS_PER_INTERACTION, "ops_executed_per_interaction": 23, "traffic": traffic,
                         "hbm_peak_gbs_measured": peaks.get("hbm_gbs")},
            "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e}
     if not args.no_cpu_baseline and world == 1:
