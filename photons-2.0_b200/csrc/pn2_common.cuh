@@ -130,7 +130,8 @@ struct pn2_ctx {
     DBuf<int> b_idx2, b_seg, b_seg2;
     DBuf<unsigned long long> b_q;    // quantised coordinates / their scan, morton keys
     DBuf<unsigned long long> b_key2;
-    DBuf<int> b_f;                   // flags / their scan
+    DBuf<int> b_f;                   // scan of the flags
+    DBuf<unsigned char> b_flag;      // flags
     DBuf<int> n_start, n_count, n_son, n_depth, l_start, l_count;   // build-time node / leaf records
     DBuf<double> n_box, n_split, l_box;                              // [cap][6] lo, hi
     DBuf<unsigned long long> b_cnt;  // per-level child counts (leaf | node << 32) and scan

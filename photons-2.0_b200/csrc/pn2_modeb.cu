@@ -7,7 +7,7 @@
 
 void pn2_modeb_release(pn2_ctx *h) {
     h->order.release(); h->parent.release(); h->depth.release(); h->b_pay.release(); h->b_pay2.release(); h->b_qc.release(); h->b_qc2.release(); h->n_sum.release(); h->b_idx2.release();
-    h->b_seg.release(); h->b_seg2.release(); h->b_q.release(); h->b_key2.release(); h->b_f.release();
+    h->b_seg.release(); h->b_seg2.release(); h->b_q.release(); h->b_key2.release(); h->b_f.release(); h->b_flag.release();
     h->n_start.release(); h->n_count.release(); h->n_son.release(); h->n_depth.release(); h->l_start.release();
     h->l_count.release(); h->n_box.release(); h->n_split.release(); h->l_box.release(); h->b_cnt.release();
     h->b_scal.release(); h->m2l_pairs.release(); h->spans.release(); h->o_head.release(); h->lst_off.release(); h->lst_src.release(); h->lst_sink.release();

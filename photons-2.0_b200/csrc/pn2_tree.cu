@@ -12,14 +12,14 @@
 //      Morton pre-sort: 63-bit key from the top 21 bits of each q, LSD radix sort (stable).  It fixes the
 //      particle order inside every leaf (the partitions below are stable).
 //   per level, direction dir = (direct0 + level) % 3, payload per particle = {qx, qy, qz, caller index}:
-//   1. exclusive prefix sum (uint64) of q_dir over all particles: a node's coordinate sum is a difference of two
-//      prefix values -- exact.  split = lo_dir + (sum / count) * 2^-(32-e) (only the boxes use the FP value).
+//   1. per-node sums of q_dir by segmented reduction + 64-bit integer atomics (nodesum_kernel) -- exact whatever the
+//      order.  split = lo_dir + (sum / count) * 2^-(32-e) (only the boxes use the FP value).
 //   2. flag_i = q_i * count > sum  ("> mean goes right", src/fmm.c:60-72; exact 64-bit products), exclusive
 //      prefix sum of the flags gives every particle its slot in a STABLE partition of its node's range.
 //   3. children: count <= MAXLEAF -> leaf, else node of the next level; ids are handed out by prefix sums over the
 //      level (breadth-first numbering, deterministic).
 //   4. scatter the 16-byte payload, the next node id and the next level's key to the other buffer.
-//   ~80 B of HBM traffic per particle per level; the FP64 positions are gathered once at the end.
+//   ~70 B of HBM traffic per particle per level; the FP64 positions are gathered once at the end.
 #include <cub/cub.cuh>
 #include "pn2_common.cuh"
 
@@ -63,34 +63,100 @@ __global__ void gather_pay_kernel(int n, const uint4 *__restrict__ pay_in, const
     seg[i] = 0;                                          // everyone starts in the root
 }
 
-// scan inputs computed on the fly
-struct KeyOf {
-    const unsigned *q; const int *seg; int n;
-    __host__ __device__ unsigned long long operator()(int i) const { return (i < n && seg[i] >= 0) ? (unsigned long long)q[i] : 0ULL; }
-};
-struct FlagOf {
-    const unsigned *q; const int *seg; const unsigned long long *n_sum; const int *n_count; int n;
-    __host__ __device__ int operator()(int i) const {
-        if (i >= n) return 0;
-        int s = seg[i];
-        if (s < 0) return 0;
-        int c = n_count[s];
-        if (c < 2) return 1;                                                 // len < 2: src/fmm.c:33-36
-        return ((unsigned long long)q[i] * (unsigned long long)c > n_sum[s]) ? 1 : 0;
+// Per-node coordinate sums without a prefix scan: the particles of a node are contiguous and `seg` (the node of a
+// particle, -1 = already in a leaf) is constant along runs, so every thread sums its 8 consecutive items run by run and
+// adds complete sums to n_sum with 64-bit integer atomics -- exact, order-independent, hence bit-reproducible.  Runs
+// that cover a whole warp / a whole block are reduced with shuffles / shared memory first (top levels: one atomic
+// per block instead of one per thread).  8 bytes of traffic per particle instead of the 16 of a 64-bit prefix scan.
+#define NS_ITEMS 8
+__global__ void __launch_bounds__(TB) nodesum_kernel(int n, const unsigned *__restrict__ q, const int *__restrict__ seg,
+                                                     unsigned long long *__restrict__ n_sum) {
+    __shared__ unsigned long long s_part[TB / 32];
+    __shared__ int s_seg[TB / 32];
+    const long base = ((long)blockIdx.x * TB + threadIdx.x) * NS_ITEMS;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned qv[NS_ITEMS];
+    int sv[NS_ITEMS];
+    if (base + NS_ITEMS <= n) {
+        const uint4 a = *reinterpret_cast<const uint4 *>(q + base), b = *reinterpret_cast<const uint4 *>(q + base + 4);
+        const int4 c = *reinterpret_cast<const int4 *>(seg + base), d = *reinterpret_cast<const int4 *>(seg + base + 4);
+        qv[0] = a.x; qv[1] = a.y; qv[2] = a.z; qv[3] = a.w; qv[4] = b.x; qv[5] = b.y; qv[6] = b.z; qv[7] = b.w;
+        sv[0] = c.x; sv[1] = c.y; sv[2] = c.z; sv[3] = c.w; sv[4] = d.x; sv[5] = d.y; sv[6] = d.z; sv[7] = d.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < NS_ITEMS; k++) {
+            const bool in = base + k < n;
+            qv[k] = in ? q[base + k] : 0u;
+            sv[k] = in ? seg[base + k] : -1;
+        }
     }
+    // runs inside the thread: complete interior runs go out directly, the last run is kept
+    int cur = sv[0];
+    unsigned long long sum = qv[0];
+    bool single = true;
+#pragma unroll
+    for (int k = 1; k < NS_ITEMS; k++) {
+        if (sv[k] != cur) {
+            if (cur >= 0) atomicAdd(&n_sum[cur], sum);
+            cur = sv[k]; sum = 0; single = false;
+        }
+        sum += qv[k];
+    }
+    // (cur, sum) = the thread's last run; if the thread is one run and so is its warp, reduce the warp first
+    const int s0 = __shfl_sync(0xffffffffu, cur, 0);
+    const bool warp_uniform = __all_sync(0xffffffffu, single && cur == s0);
+    if (!warp_uniform) {
+        if (cur >= 0) atomicAdd(&n_sum[cur], sum);
+        sum = 0; cur = -2;                                   // nothing left for the block stage
+    } else {
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, m);
+    }
+    if (lane == 0) { s_part[wid] = sum; s_seg[wid] = cur; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // consecutive warps of one run are merged: one atomic per run and block
+        int rs = s_seg[0];
+        unsigned long long rsum = s_part[0];
+        for (int w = 1; w < TB / 32; w++) {
+            if (s_seg[w] != rs) {
+                if (rs >= 0) atomicAdd(&n_sum[rs], rsum);
+                rs = s_seg[w]; rsum = 0;
+            }
+            rsum += s_part[w];
+        }
+        if (rs >= 0) atomicAdd(&n_sum[rs], rsum);
+    }
+}
+
+// flag_i = "particle i goes right" = q_i * count > sum (exact 64-bit products; src/fmm.c:60-72), as a byte; the
+// prefix sum of the flags (CUB, over the byte array) gives every particle its slot in the stable partition
+__global__ void flag_kernel(int n, const unsigned *__restrict__ q, const int *__restrict__ seg,
+                            const unsigned long long *__restrict__ n_sum, const int *__restrict__ n_count,
+                            unsigned char *__restrict__ flag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    unsigned char f = 0;
+    if (i < n) {
+        const int s = seg[i];
+        if (s >= 0) {
+            const int c = n_count[s];
+            f = (c < 2) ? 1 : (((unsigned long long)q[i] * (unsigned long long)c > n_sum[s]) ? 1 : 0);     // len < 2: src/fmm.c:33-36
+        }
+    }
+    flag[i] = f;
+}
+struct ByteToInt {
+    __host__ __device__ int operator()(unsigned char v) const { return (int)v; }
 };
 
-// one thread per node of the level: coordinate sum and split position
-__global__ void split_kernel(int cnt, int node0, const int *__restrict__ n_start, const int *__restrict__ n_count,
-                             const unsigned long long *__restrict__ Sq, double lo, double invS,
-                             unsigned long long *__restrict__ n_sum, double *__restrict__ n_split) {
+// one thread per node of the level: split position from the node's coordinate sum
+__global__ void split_kernel(int cnt, int node0, const int *__restrict__ n_count, const unsigned long long *__restrict__ n_sum,
+                             double lo, double invS, double *__restrict__ n_split) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= cnt) return;
     int nd = node0 + k;
-    int a = n_start[nd], c = n_count[nd];
-    unsigned long long sum = Sq[a + c] - Sq[a];
-    n_sum[nd] = sum;
-    double m = __ddiv_rn(__ull2double_rn(sum), (double)c);
+    double m = __ddiv_rn(__ull2double_rn(n_sum[nd]), (double)n_count[nd]);
     n_split[nd] = __dadd_rn(lo, __dmul_rn(m, invS));
 }
 
@@ -117,7 +183,7 @@ __global__ void children_kernel(int cnt, int node0, int next_node0, int leaf0, i
                                 int *__restrict__ n_depth, double *__restrict__ n_box, const double *__restrict__ n_split,
                                 int *__restrict__ l_start, int *__restrict__ l_count, double *__restrict__ l_box,
                                 const int *__restrict__ F, const unsigned long long *__restrict__ ccs, int node_cap,
-                                int leaf_cap, int *__restrict__ scal) {
+                                int leaf_cap, int *__restrict__ scal, unsigned long long *__restrict__ n_sum) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= cnt) return;
     int nd = node0 + k;
@@ -146,7 +212,7 @@ __global__ void children_kernel(int cnt, int node0, int next_node0, int leaf0, i
             li++;
         } else {
             if (ni < node_cap) {
-                n_start[ni] = st[s]; n_count[ni] = cn[s]; n_depth[ni] = depth + 1;
+                n_start[ni] = st[s]; n_count[ni] = cn[s]; n_depth[ni] = depth + 1; n_sum[ni] = 0ULL;
 #pragma unroll
                 for (int d = 0; d < 6; d++) n_box[6 * (size_t)ni + d] = cb[d];
             } else atomicExch(&scal[3], 1);
@@ -246,7 +312,7 @@ int pn2_tree_build_device(pn2_ctx *h, const double *d_pos_in, int n, const pn2_d
     PN2_TRY(h->acc.ensure(3 * (size_t)n + 3)); PN2_TRY(h->rel.ensure((size_t)n + 1));
     PN2_TRY(h->order.ensure(n + 1)); PN2_TRY(h->b_idx2.ensure(n + 1));
     PN2_TRY(h->b_seg.ensure(n + 1)); PN2_TRY(h->b_seg2.ensure(n + 1));
-    PN2_TRY(h->b_q.ensure(n + 2)); PN2_TRY(h->b_key2.ensure(n + 2)); PN2_TRY(h->b_f.ensure(n + 2));
+    PN2_TRY(h->b_q.ensure(n + 2)); PN2_TRY(h->b_key2.ensure(n + 2)); PN2_TRY(h->b_f.ensure(n + 2)); PN2_TRY(h->b_flag.ensure((size_t)n + 16));
     PN2_TRY(h->b_pay.ensure((size_t)n + 1)); PN2_TRY(h->b_pay2.ensure((size_t)n + 1));
     PN2_TRY(h->b_qc.ensure((size_t)n + 1)); PN2_TRY(h->b_qc2.ensure((size_t)n + 1));
     PN2_TRY(h->b_scal.ensure(16));
@@ -270,18 +336,12 @@ int pn2_tree_build_device(pn2_ctx *h, const double *d_pos_in, int n, const pn2_d
 
     // ---- 0. quantise + Morton pre-sort ----
     quant_morton_kernel<<<nb(n), TB, 0, st>>>(n, d_pos_in, dom->lo[0], dom->lo[1], dom->lo[2], S, h->b_pay2.p, h->b_q.p, h->b_idx2.p);
-    KeyOf keyf{h->b_qc.p, h->b_seg.p, n};
-    FlagOf flagf{h->b_qc.p, h->b_seg.p, h->n_sum.p, h->n_count.p, n};
-    cub::CountingInputIterator<int> cnt_it(0);
-    cub::TransformInputIterator<unsigned long long, KeyOf, cub::CountingInputIterator<int>> key_it(cnt_it, keyf);
-    cub::TransformInputIterator<int, FlagOf, cub::CountingInputIterator<int>> flag_it(cnt_it, flagf);
-    size_t tb = 0, tb2 = 0, tb3 = 0, tb4 = 0;
+    cub::TransformInputIterator<int, ByteToInt, const unsigned char *> flag_it(h->b_flag.p, ByteToInt());
+    size_t tb = 0, tb3 = 0, tb4 = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tb, h->b_q.p, h->b_key2.p, h->b_idx2.p, h->order.p, n, 0, 63, st);
-    cub::DeviceScan::ExclusiveSum(nullptr, tb2, key_it, h->b_key2.p, n + 1, st);
     cub::DeviceScan::ExclusiveSum(nullptr, tb3, flag_it, h->b_f.p, n + 1, st);
     cub::DeviceScan::ExclusiveSum(nullptr, tb4, h->b_q.p, h->b_q.p, cap + 1, st);
     size_t need = tb;
-    if (tb2 > need) need = tb2;
     if (tb3 > need) need = tb3;
     if (tb4 > need) need = tb4;
     PN2_TRY(h->tmp.ensure(need + 16));
@@ -300,6 +360,7 @@ int pn2_tree_build_device(pn2_ctx *h, const double *d_pos_in, int n, const pn2_d
         CUDA_TRY(cudaMemcpyAsync(h->n_son.p, m1, 2 * sizeof(int), cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(h->n_box.p, box, 6 * sizeof(double), cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemsetAsync(h->b_scal.p, 0, 16 * sizeof(int), st));
+        CUDA_TRY(cudaMemsetAsync(h->n_sum.p, 0, sizeof(unsigned long long), st));
         CUDA_TRY(cudaStreamSynchronize(st));
     }
 
@@ -312,20 +373,17 @@ int pn2_tree_build_device(pn2_ctx *h, const double *d_pos_in, int n, const pn2_d
         if (level > 200) { pn2_set_error("pn2: tree deeper than 200 levels (more than MAXLEAF coincident particles?)"); return PN2_ERR_ARG; }
         int dir = (dom->direct0 + level) % 3;
         double lo = dom->lo[dir];
-        keyf.q = qc; keyf.seg = sg;
-        flagf.q = qc; flagf.seg = sg;
-        cub::TransformInputIterator<unsigned long long, KeyOf, cub::CountingInputIterator<int>> kit(cnt_it, keyf);
-        cub::TransformInputIterator<int, FlagOf, cub::CountingInputIterator<int>> fit(cnt_it, flagf);
-        cub::DeviceScan::ExclusiveSum(h->tmp.p, tb2, kit, h->b_key2.p, n + 1, st);
-        split_kernel<<<nb(cnt), TB, 0, st>>>(cnt, node0, h->n_start.p, h->n_count.p, h->b_key2.p, lo, invS, h->n_sum.p, h->n_split.p);
-        cub::DeviceScan::ExclusiveSum(h->tmp.p, tb3, fit, h->b_f.p, n + 1, st);
+        nodesum_kernel<<<nb(((long)n + NS_ITEMS - 1) / NS_ITEMS), TB, 0, st>>>(n, qc, sg, h->n_sum.p);
+        split_kernel<<<nb(cnt), TB, 0, st>>>(cnt, node0, h->n_count.p, h->n_sum.p, lo, invS, h->n_split.p);
+        flag_kernel<<<nb((long)n + 1), TB, 0, st>>>(n, qc, sg, h->n_sum.p, h->n_count.p, h->b_flag.p);
+        cub::DeviceScan::ExclusiveSum(h->tmp.p, tb3, flag_it, h->b_f.p, n + 1, st);
         childcount_kernel<<<nb(cnt + 1), TB, 0, st>>>(cnt, node0, h->n_start.p, h->n_count.p, h->b_f.p, maxleaf, h->b_q.p);
         cub::DeviceScan::ExclusiveSum(h->tmp.p, tb4, h->b_q.p, h->b_q.p, cnt + 1, st);
         children_kernel<<<nb(cnt), TB, 0, st>>>(cnt, node0, node0 + cnt, nleaf, dir, level, maxleaf, h->n_start.p, h->n_count.p,
                                                 h->n_son.p, h->n_depth.p, h->n_box.p, h->n_split.p, h->l_start.p,
-                                                h->l_count.p, h->l_box.p, h->b_f.p, h->b_q.p, cap, cap, h->b_scal.p);
+                                                h->l_count.p, h->l_box.p, h->b_f.p, h->b_q.p, cap, cap, h->b_scal.p, h->n_sum.p);
         scatter_kernel<<<nb(n), TB, 0, st>>>(n, pc, sg, h->b_f.p, h->n_start.p, h->n_count.p, h->n_son.p, (dir + 1) % 3, po, so, qo);
-        h->launches += 7;
+        h->launches += 8;
         int hs[4];
         CUDA_TRY(cudaMemcpyAsync(hs, h->b_scal.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));

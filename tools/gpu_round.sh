@@ -1,7 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-( timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6 ) | tee gpurun_out/pytest_gpu_r01i.log
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4 | tee gpurun_out/smoke_r01i.log
-python bench.py > gpurun_out/bench_512_r01i.json 2> gpurun_out/bench_512_r01i.err; tail -c 1200 gpurun_out/bench_512_r01i.json
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_r01i.json 2> gpurun_out/bench_ref_r01i.err; tail -c 300 gpurun_out/bench_ref_r01i.json
-timeout 900 bash tools/profile.sh r01i 256
+( timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6 ) | tee gpurun_out/pytest_gpu.log
+for s in 256 512; do timeout 300 python bench.py --npart-side $s --steps 3 --warmup 2 --no-cpu-baseline --no-e2e 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('pps %.4g ms %.2f'%(d['value'], d['ms_per_step']), {k:round(v,2) for k,v in d['phases_ms'].items()}, 'frac %.3f'%d['roofline']['frac'])"; done
