@@ -1,84 +1,135 @@
 // pn2_operators.cu -- P2M / M2M / M2L / L2L / L2P kernels (FP64) over the cell arrays.
 //
-// These are <1 % of a force step; they are HBM-bound streaming kernels over
-// 160-byte multipole / local-expansion records, one thread per cell, level-synchronous where the
-// reference recurses (walk_m2m: src/operator.c:165-194, walk_l2l: src/operator.c:498-528).
+// These are a few % of a force step; they are HBM-bound streaming kernels over
+// 160-byte multipole / local-expansion records, one thread per cell (records moved by the warp, see
+// warp_load_records), level-synchronous where the reference recurses (walk_m2m: src/operator.c:165-194, walk_l2l: src/operator.c:498-528).
 #include "pn2_operators.cuh"
 
 using namespace pn2op;
 
+// The 160-byte M / L records are read and written by the WARP, not by the thread: lane l wants record idx_l; the
+// warp moves the 32 records as 320 chunks of 16 bytes (lane-consecutive chunks are address-consecutive inside a
+// record, and consecutive cells are consecutive records), through a padded shared-memory tile from which every lane
+// picks its own 20 values.  A thread-per-record access pattern touches 32 different sectors per load instruction.
+#define OP_WARPS 4
+#define REC_STRIDE (NM + 1)               // doubles per record in shared memory (+1: bank spread)
+__device__ __forceinline__ void warp_load_records(const double *__restrict__ base, int idx, double (&v)[NM], double *tile, int lane) {
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < NM / 2; t++) {
+        const int c = t * 32 + lane, r = c / (NM / 2), k = c % (NM / 2);
+        const int ri = __shfl_sync(0xffffffffu, idx, r);
+        if (ri >= 0) {
+            const double2 d = *reinterpret_cast<const double2 *>(base + (size_t)ri * NM + 2 * k);
+            tile[r * REC_STRIDE + 2 * k] = d.x;
+            tile[r * REC_STRIDE + 2 * k + 1] = d.y;
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < NM; i++) v[i] = idx >= 0 ? tile[lane * REC_STRIDE + i] : 0.0;
+}
+__device__ __forceinline__ void warp_store_records(double *__restrict__ base, int idx, const double (&v)[NM], double *tile, int lane) {
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < NM; i++) tile[lane * REC_STRIDE + i] = v[i];
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < NM / 2; t++) {
+        const int c = t * 32 + lane, r = c / (NM / 2), k = c % (NM / 2);
+        const int ri = __shfl_sync(0xffffffffu, idx, r);
+        if (ri >= 0)
+            *reinterpret_cast<double2 *>(base + (size_t)ri * NM + 2 * k) = make_double2(tile[r * REC_STRIDE + 2 * k], tile[r * REC_STRIDE + 2 * k + 1]);
+    }
+}
+
 // ---- P2M: one thread per leaf (src/fmm.c:741-742 -> src/operator.c:13-93) ----
-__global__ void p2m_kernel(int nleaf, const LeafDesc *__restrict__ desc, const double *__restrict__ pos, double mass,
-                           double *__restrict__ M) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= nleaf) return;
-    LeafDesc d = desc[k];
+__global__ void __launch_bounds__(OP_WARPS * 32) p2m_kernel(int nleaf, const LeafDesc *__restrict__ desc, const double *__restrict__ pos,
+                                                            double mass, double *__restrict__ M) {
+    __shared__ double s_tile[OP_WARPS][32 * REC_STRIDE];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool on = k < nleaf;
     double m[NM];
 #pragma unroll
     for (int i = 0; i < NM; i++) m[i] = 0.0;
-    for (int p = d.first; p < d.first + d.npart; p++)
-        p2m_add(pos[3 * p] - d.c[0], pos[3 * p + 1] - d.c[1], pos[3 * p + 2] - d.c[2], mass, m);
-#pragma unroll
-    for (int i = 0; i < NM; i++) M[(size_t)k * NM + i] = m[i];
+    if (on) {
+        const LeafDesc d = desc[k];
+        for (int p = d.first; p < d.first + d.npart; p++)
+            p2m_add(pos[3 * (size_t)p] - d.c[0], pos[3 * (size_t)p + 1] - d.c[1], pos[3 * (size_t)p + 2] - d.c[2], mass, m);
+    }
+    warp_store_records(M, on ? k : -1, m, s_tile[wib], lane);
 }
 
 // ---- M2M: one thread per node of one depth; children are finished (deeper levels ran first) ----
-__global__ void m2m_level_kernel(int cnt, const int *__restrict__ nodes, const int *__restrict__ son,
-                                 const double *__restrict__ geom, double *__restrict__ M) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= cnt) return;
-    int c = nodes[k];
+__global__ void __launch_bounds__(OP_WARPS * 32) m2m_level_kernel(int cnt, const int *__restrict__ nodes, const int *__restrict__ son,
+                                                                  const double *__restrict__ geom, double *__restrict__ M) {
+    __shared__ double s_tile[OP_WARPS][32 * REC_STRIDE];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool on = k < cnt;
+    const int c = on ? nodes[k] : -1;
     double m[NM];
 #pragma unroll
     for (int i = 0; i < NM; i++) m[i] = 0.0;
-    double cx = geom[6 * (size_t)c], cy = geom[6 * (size_t)c + 1], cz = geom[6 * (size_t)c + 2];
-    for (int s = 0; s < 2; s++) {
-        int ch = son[2 * (size_t)c + s];
-        if (ch < 0) continue;
-        double cm[NM];
-#pragma unroll
-        for (int i = 0; i < NM; i++) cm[i] = M[(size_t)ch * NM + i];
-        m2m_add(cx - geom[6 * (size_t)ch], cy - geom[6 * (size_t)ch + 1], cz - geom[6 * (size_t)ch + 2], cm, m);
+    double cx = 0, cy = 0, cz = 0;
+    int2 ch = make_int2(-1, -1);
+    if (on) {
+        cx = geom[6 * (size_t)c]; cy = geom[6 * (size_t)c + 1]; cz = geom[6 * (size_t)c + 2];
+        ch = *reinterpret_cast<const int2 *>(son + 2 * (size_t)c);
     }
 #pragma unroll
-    for (int i = 0; i < NM; i++) M[(size_t)c * NM + i] = m[i];
+    for (int s = 0; s < 2; s++) {
+        const int cs = s == 0 ? ch.x : ch.y;
+        double cm[NM];
+        warp_load_records(M, cs, cm, s_tile[wib], lane);
+        if (cs >= 0) m2m_add(cx - geom[6 * (size_t)cs], cy - geom[6 * (size_t)cs + 1], cz - geom[6 * (size_t)cs + 2], cm, m);
+    }
+    warp_store_records(M, c, m, s_tile[wib], lane);
 }
 
 // ---- L2L: one thread per node of one depth, pushes its L into both children ----
-__global__ void l2l_level_kernel(int cnt, const int *__restrict__ nodes, const int *__restrict__ son,
-                                 const double *__restrict__ geom, double *__restrict__ L) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= cnt) return;
-    int c = nodes[k];
+__global__ void __launch_bounds__(OP_WARPS * 32) l2l_level_kernel(int cnt, const int *__restrict__ nodes, const int *__restrict__ son,
+                                                                  const double *__restrict__ geom, double *__restrict__ L) {
+    __shared__ double s_tile[OP_WARPS][32 * REC_STRIDE];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool on = k < cnt;
+    const int c = on ? nodes[k] : -1;
     double l[NM];
+    warp_load_records(L, c, l, s_tile[wib], lane);
+    double cx = 0, cy = 0, cz = 0;
+    int2 ch = make_int2(-1, -1);
+    if (on) {
+        cx = geom[6 * (size_t)c]; cy = geom[6 * (size_t)c + 1]; cz = geom[6 * (size_t)c + 2];
+        ch = *reinterpret_cast<const int2 *>(son + 2 * (size_t)c);
+        if (ch.x < 0) ch.y = -1;                    // src/operator.c:524-525 returns at the first missing son
+    }
 #pragma unroll
-    for (int i = 0; i < NM; i++) l[i] = L[(size_t)c * NM + i];
-    double cx = geom[6 * (size_t)c], cy = geom[6 * (size_t)c + 1], cz = geom[6 * (size_t)c + 2];
     for (int s = 0; s < 2; s++) {
-        int ch = son[2 * (size_t)c + s];
-        if (ch < 0) return;                         // src/operator.c:524-525 returns at the first missing son
+        const int cs = s == 0 ? ch.x : ch.y;
         double cl[NM];
-#pragma unroll
-        for (int i = 0; i < NM; i++) cl[i] = L[(size_t)ch * NM + i];
-        l2l_add(geom[6 * (size_t)ch] - cx, geom[6 * (size_t)ch + 1] - cy, geom[6 * (size_t)ch + 2] - cz, l, cl);
-#pragma unroll
-        for (int i = 0; i < NM; i++) L[(size_t)ch * NM + i] = cl[i];
+        warp_load_records(L, cs, cl, s_tile[wib], lane);
+        if (cs >= 0) l2l_add(geom[6 * (size_t)cs] - cx, geom[6 * (size_t)cs + 1] - cy, geom[6 * (size_t)cs + 2] - cz, l, cl);
+        warp_store_records(L, cs, cl, s_tile[wib], lane);
     }
 }
 
 // ---- L2P: one thread per leaf (src/fmm.c:1056-1057 -> src/operator.c:197-251) ----
-__global__ void l2p_kernel(int nleaf, const LeafDesc *__restrict__ desc, const double *__restrict__ pos,
-                           const double *__restrict__ L, double *__restrict__ acc) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= nleaf) return;
-    LeafDesc d = desc[k];
+__global__ void __launch_bounds__(OP_WARPS * 32) l2p_kernel(int nleaf, const LeafDesc *__restrict__ desc, const double *__restrict__ pos,
+                                                            const double *__restrict__ L, double *__restrict__ acc) {
+    __shared__ double s_tile[OP_WARPS][32 * REC_STRIDE];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool on = k < nleaf;
     double l[NM];
-#pragma unroll
-    for (int i = 0; i < NM; i++) l[i] = L[(size_t)k * NM + i];
+    warp_load_records(L, on ? k : -1, l, s_tile[wib], lane);
+    if (!on) return;
+    const LeafDesc d = desc[k];
     for (int p = d.first; p < d.first + d.npart; p++) {
         double a[3];
-        l2p_eval(pos[3 * p] - d.c[0], pos[3 * p + 1] - d.c[1], pos[3 * p + 2] - d.c[2], l, a);
-        acc[3 * p] += a[0]; acc[3 * p + 1] += a[1]; acc[3 * p + 2] += a[2];
+        l2p_eval(pos[3 * (size_t)p] - d.c[0], pos[3 * (size_t)p + 1] - d.c[1], pos[3 * (size_t)p + 2] - d.c[2], l, a);
+        acc[3 * (size_t)p] += a[0]; acc[3 * (size_t)p + 1] += a[1]; acc[3 * (size_t)p + 2] += a[2];
     }
 }
 
@@ -114,7 +165,7 @@ static inline int nblk(long n, int b) { return (int)((n + b - 1) / b); }
 
 int pn2_launch_p2m(pn2_ctx *h) {
     if (h->nleaf == 0) return PN2_OK;
-    p2m_kernel<<<nblk(h->nleaf, 128), 128, 0, h->stream>>>(h->nleaf, h->desc.p, h->pos.p, h->prm.mass, h->M.p);
+    p2m_kernel<<<nblk(h->nleaf, OP_WARPS * 32), OP_WARPS * 32, 0, h->stream>>>(h->nleaf, h->desc.p, h->pos.p, h->prm.mass, h->M.p);
     h->launches++;
     KERNEL_CHECK();
     return PN2_OK;
@@ -124,7 +175,7 @@ int pn2_launch_m2m(pn2_ctx *h) {
     for (int lev = h->nlevel - 1; lev >= 0; lev--) {
         int cnt = h->level_off[lev + 1] - h->level_off[lev];
         if (cnt == 0) continue;
-        m2m_level_kernel<<<nblk(cnt, 128), 128, 0, h->stream>>>(cnt, h->level_nodes.p + h->level_off[lev], h->son.p,
+        m2m_level_kernel<<<nblk(cnt, OP_WARPS * 32), OP_WARPS * 32, 0, h->stream>>>(cnt, h->level_nodes.p + h->level_off[lev], h->son.p,
                                                                 h->geom.p, h->M.p);
         h->launches++;
     }
@@ -136,12 +187,12 @@ int pn2_launch_l2l_l2p(pn2_ctx *h) {
     for (int lev = 0; lev < h->nlevel; lev++) {
         int cnt = h->level_off[lev + 1] - h->level_off[lev];
         if (cnt == 0) continue;
-        l2l_level_kernel<<<nblk(cnt, 128), 128, 0, h->stream>>>(cnt, h->level_nodes.p + h->level_off[lev], h->son.p,
+        l2l_level_kernel<<<nblk(cnt, OP_WARPS * 32), OP_WARPS * 32, 0, h->stream>>>(cnt, h->level_nodes.p + h->level_off[lev], h->son.p,
                                                                 h->geom.p, h->L.p);
         h->launches++;
     }
     if (h->nleaf > 0) {
-        l2p_kernel<<<nblk(h->nleaf, 128), 128, 0, h->stream>>>(h->nleaf, h->desc.p, h->pos.p, h->L.p, h->acc.p);
+        l2p_kernel<<<nblk(h->nleaf, OP_WARPS * 32), OP_WARPS * 32, 0, h->stream>>>(h->nleaf, h->desc.p, h->pos.p, h->L.p, h->acc.p);
         h->launches++;
     }
     KERNEL_CHECK();
