@@ -134,17 +134,37 @@ __global__ void __launch_bounds__(TB) nodesum_kernel(int n, const unsigned *__re
 __global__ void flag_kernel(int n, const unsigned *__restrict__ q, const int *__restrict__ seg,
                             const unsigned long long *__restrict__ n_sum, const int *__restrict__ n_count,
                             unsigned char *__restrict__ flag) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > n) return;
-    unsigned char f = 0;
-    if (i < n) {
-        const int s = seg[i];
-        if (s >= 0) {
-            const int c = n_count[s];
-            f = (c < 2) ? 1 : (((unsigned long long)q[i] * (unsigned long long)c > n_sum[s]) ? 1 : 0);     // len < 2: src/fmm.c:33-36
+    const long base = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;     // 4 items per thread: 16-byte loads, 4-byte store
+    if (base > n) return;
+    unsigned qv[4];
+    int sv[4];
+    if (base + 4 <= n) {
+        const uint4 a = *reinterpret_cast<const uint4 *>(q + base);
+        const int4 c = *reinterpret_cast<const int4 *>(seg + base);
+        qv[0] = a.x; qv[1] = a.y; qv[2] = a.z; qv[3] = a.w;
+        sv[0] = c.x; sv[1] = c.y; sv[2] = c.z; sv[3] = c.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const bool in = base + k < n;
+            qv[k] = in ? q[base + k] : 0u;
+            sv[k] = in ? seg[base + k] : -1;
         }
     }
-    flag[i] = f;
+    unsigned char f[4];
+    int ls = -1, lc = 0;
+    unsigned long long lsum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        f[k] = 0;
+        const int s = sv[k];
+        if (s >= 0) {
+            if (s != ls) { ls = s; lc = n_count[s]; lsum = n_sum[s]; }       // consecutive particles share their node
+            f[k] = (lc < 2) ? 1 : (((unsigned long long)qv[k] * (unsigned long long)lc > lsum) ? 1 : 0);    // len < 2: src/fmm.c:33-36
+        }
+    }
+    // flag[] has n + 1 entries (the scan runs over n + 1 items); the buffer is padded to a multiple of 4
+    *reinterpret_cast<uchar4 *>(flag + base) = make_uchar4(f[0], f[1], f[2], f[3]);
 }
 struct ByteToInt {
     __host__ __device__ int operator()(unsigned char v) const { return (int)v; }
@@ -375,7 +395,7 @@ int pn2_tree_build_device(pn2_ctx *h, const double *d_pos_in, int n, const pn2_d
         double lo = dom->lo[dir];
         nodesum_kernel<<<nb(((long)n + NS_ITEMS - 1) / NS_ITEMS), TB, 0, st>>>(n, qc, sg, h->n_sum.p);
         split_kernel<<<nb(cnt), TB, 0, st>>>(cnt, node0, h->n_count.p, h->n_sum.p, lo, invS, h->n_split.p);
-        flag_kernel<<<nb((long)n + 1), TB, 0, st>>>(n, qc, sg, h->n_sum.p, h->n_count.p, h->b_flag.p);
+        flag_kernel<<<nb(((long)n + 4) / 4), TB, 0, st>>>(n, qc, sg, h->n_sum.p, h->n_count.p, h->b_flag.p);
         cub::DeviceScan::ExclusiveSum(h->tmp.p, tb3, flag_it, h->b_f.p, n + 1, st);
         childcount_kernel<<<nb(cnt + 1), TB, 0, st>>>(cnt, node0, h->n_start.p, h->n_count.p, h->b_f.p, maxleaf, h->b_q.p);
         cub::DeviceScan::ExclusiveSum(h->tmp.p, tb4, h->b_q.p, h->b_q.p, cnt + 1, st);
