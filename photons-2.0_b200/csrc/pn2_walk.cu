@@ -291,8 +291,8 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NODE_MIN_BLOCKS) frontier_nod
 //     FP32 mode (MODE 0): {tile, dx, dy, dz}  tile = leaf tile index, d = source leaf centre - sink leaf centre
 //                                             (+ image shift) in units of lambda = 2 rs sqrt(ln 2)
 //     FP64 / dump modes : {first, npart, cell | image << 26, 0}
-template <int MODE, int U, int QCAP>     // U = stack entries per lane and step (32 U per step): the walk is latency-bound,
-struct LeafWalk {                        // wider steps mean fewer dependent round trips per leaf; QCAP = queue capacity
+template <int MODE, int QCAP>      // QCAP = queue capacity: a power of two > (entries a consumer leaves queued, < 32) + 32
+struct LeafWalk {
     SpanReader rd;
     unsigned *stack;
     int4 *queue;
@@ -313,91 +313,81 @@ struct LeafWalk {                        // wider steps mean fewer dependent rou
         ssize = 0; qtail = 0; err = 0; nsrc = 0; visits = 0; npairs = 0;
         __syncwarp();
     }
-    // returns false when F(leaf) is exhausted (or the stack overflowed: err)
+    // one step = up to 32 entries of the stack; returns false when F(leaf) is exhausted (or the stack overflowed: err)
     __device__ __forceinline__ bool step(const WalkArgs &a, const P2PConst &pc, int lane) {
         const unsigned lt_mask = (1u << lane) - 1u;
-        while (ssize < 32 * U && pre_n > 0) {
+        while (ssize < 32 && pre_n > 0) {
             if (lane < pre_n) stack[ssize + lane] = pre_e;
             ssize += pre_n;
             pre_n = rd.fetch(lane, pre_e);
             __syncwarp();
         }
         if (ssize == 0) return false;
-        int k = ssize < 32 * U ? ssize : 32 * U;
+        int k = ssize < 32 ? ssize : 32;
         if (k > STACK_CAP - ssize) k = STACK_CAP - ssize > 0 ? STACK_CAP - ssize : 1;     // every entry can grow the stack by one
         const int sbase = ssize - k;
         // ---- phase 1: every global load of the step is requested before any of them is used (one round trip):
         //      a leaf's descriptor {centre, first, npart} or a node's geometry {centre, width} + sons
-        unsigned jme[U];
-        bool lj[U];
-        double2 r0[U], r1[U], r2[U];
-        int2 sons[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            jme[u] = 0; lj[u] = false;
-            r0[u] = r1[u] = r2[u] = make_double2(0.0, 0.0);
-            sons[u] = make_int2(0, 0);
-            if (u * 32 + lane < k) {
-                jme[u] = stack[sbase + u * 32 + lane];
-                const int jm = (int)(jme[u] & PN2_CELL_MASK);
-                lj[u] = jm < a.nleaf || (jm >= a.rleaf0 && jm < a.rnode0);
-                const double2 *rec = lj[u] ? reinterpret_cast<const double2 *>(a.desc + jm) : reinterpret_cast<const double2 *>(a.geom + 6 * (size_t)jm);
-                r0[u] = rec[0]; r1[u] = rec[1];
-                if (!lj[u]) { r2[u] = rec[2]; sons[u] = *reinterpret_cast<const int2 *>(a.son + 2 * (size_t)jm); }
-            }
+        unsigned jme = 0;
+        bool lj = false;
+        double2 r0 = make_double2(0.0, 0.0), r1 = r0, r2 = r0;
+        int2 sons = make_int2(0, 0);
+        if (lane < k) {
+            jme = stack[sbase + lane];
+            const int jm = (int)(jme & PN2_CELL_MASK);
+            lj = jm < a.nleaf || (jm >= a.rleaf0 && jm < a.rnode0);
+            const double2 *rec = lj ? reinterpret_cast<const double2 *>(a.desc + jm) : reinterpret_cast<const double2 *>(a.geom + 6 * (size_t)jm);
+            r0 = rec[0]; r1 = rec[1];
+            if (!lj) { r2 = rec[2]; sons = *reinterpret_cast<const int2 *>(a.son + 2 * (size_t)jm); }
         }
         visits += k;
         __syncwarp();                      // the popped entries are in registers: the stack may be overwritten from sbase
         // ---- phase 2: decide, then compact pushes / queue entries / M2L pairs with ballots ----
-        int top = sbase;
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            int npush = 0, emit_p = 0, emit_m = 0;
-            unsigned p0 = 0, p1 = 0;
-            int4 ent = make_int4(0, 0, 0, 0);
-            if (u * 32 + lane < k) {
-                const int jm = (int)(jme[u] & PN2_CELL_MASK);
-                const unsigned img = jme[u] >> PN2_IMG_SHIFT, imgbits = jme[u] & ~PN2_CELL_MASK;
-                if (lj[u]) {
-                    // leaf x leaf: always a P2P pair (src/fmm.c:438-451, src/remotes.c:228-240)
-                    emit_p = 1;
-                    const int dfirst = __double2loint(r1[u].y), dnpart = __double2hiint(r1[u].y);
-                    if (MODE == 0) {
-                        ent.x = jm < a.nleaf ? jm : jm - a.rleaf0 + a.nleaf;
-                        ent.y = __float_as_int((float)(((r0[u].x + pc.shift[img][0]) - sd.c[0]) * pc.inv_len));
-                        ent.z = __float_as_int((float)(((r0[u].y + pc.shift[img][1]) - sd.c[1]) * pc.inv_len));
-                        ent.w = __float_as_int((float)(((r1[u].x + pc.shift[img][2]) - sd.c[2]) * pc.inv_len));
-                    } else {
-                        ent = make_int4(dfirst, dnpart, (int)jme[u], 0);
-                    }
-                    nsrc += (unsigned)(dnpart - ((jme[u] == (unsigned)leaf) ? 1 : 0));
+        int npush = 0, emit_p = 0, emit_m = 0;
+        unsigned p0 = 0, p1 = 0;
+        int4 ent = make_int4(0, 0, 0, 0);
+        if (lane < k) {
+            const int jm = (int)(jme & PN2_CELL_MASK);
+            const unsigned img = jme >> PN2_IMG_SHIFT, imgbits = jme & ~PN2_CELL_MASK;
+            if (lj) {
+                // leaf x leaf: always a P2P pair (src/fmm.c:438-451, src/remotes.c:228-240)
+                emit_p = 1;
+                const int dfirst = __double2loint(r1.y), dnpart = __double2hiint(r1.y);
+                if (MODE == 0) {
+                    ent.x = jm < a.nleaf ? jm : jm - a.rleaf0 + a.nleaf;
+                    ent.y = __float_as_int((float)(((r0.x + pc.shift[img][0]) - sd.c[0]) * pc.inv_len));
+                    ent.z = __float_as_int((float)(((r0.y + pc.shift[img][1]) - sd.c[1]) * pc.inv_len));
+                    ent.w = __float_as_int((float)(((r1.x + pc.shift[img][2]) - sd.c[2]) * pc.inv_len));
                 } else {
-                    double cj[3] = {r0[u].x, r0[u].y, r1[u].x}, wj[3] = {r1[u].y, r2[u].x, r2[u].y};
-                    int pruned = 0;
-                    if (img != 0 || jm >= a.rleaf0) {
-                        pruned = pruned_dev(cj, wj, pc.shift[img], a.tc, a.tw, a.cutoff, a.theta, a.longshort);
-                        cj[0] += pc.shift[img][0]; cj[1] += pc.shift[img][1]; cj[2] += pc.shift[img][2];
-                    }
-                    int f = accept_dev(sink_g + 3, wj, sink_g[0] - cj[0], sink_g[1] - cj[1], sink_g[2] - cj[2], a.cutoff, a.theta,
-                                       a.longshort);
-                    if (f == 1 || (f == 0 && pruned)) emit_m = 1;        // forced M2L on a pruned node: src/remotes.c:442
-                    else if (f == 0) {
-                        npush = 2;
-                        p0 = (unsigned)sons[u].x | imgbits; p1 = (unsigned)sons[u].y | imgbits;
-                    }
+                    ent = make_int4(dfirst, dnpart, (int)jme, 0);
+                }
+                nsrc += (unsigned)(dnpart - ((jme == (unsigned)leaf) ? 1 : 0));
+            } else {
+                double cj[3] = {r0.x, r0.y, r1.x}, wj[3] = {r1.y, r2.x, r2.y};
+                int pruned = 0;
+                if (img != 0 || jm >= a.rleaf0) {
+                    pruned = pruned_dev(cj, wj, pc.shift[img], a.tc, a.tw, a.cutoff, a.theta, a.longshort);
+                    cj[0] += pc.shift[img][0]; cj[1] += pc.shift[img][1]; cj[2] += pc.shift[img][2];
+                }
+                const int f = accept_dev(sink_g + 3, wj, sink_g[0] - cj[0], sink_g[1] - cj[1], sink_g[2] - cj[2], a.cutoff, a.theta,
+                                         a.longshort);
+                if (f == 1 || (f == 0 && pruned)) emit_m = 1;        // forced M2L on a pruned node: src/remotes.c:442
+                else if (f == 0) {
+                    npush = 2;
+                    p0 = (unsigned)sons.x | imgbits; p1 = (unsigned)sons.y | imgbits;
                 }
             }
-            const unsigned m2 = __ballot_sync(0xffffffffu, npush == 2);
-            const int pos0 = top + 2 * __popc(m2 & lt_mask);
-            top += 2 * __popc(m2);
-            if (top > STACK_CAP) { err = 1; return false; }
-            if (npush == 2) { stack[pos0] = p0; stack[pos0 + 1] = p1; }
-            const unsigned mp = __ballot_sync(0xffffffffu, emit_p);
-            if (emit_p) queue[(qtail + __popc(mp & lt_mask)) & (QCAP - 1)] = ent;
-            qtail += __popc(mp);
-            npairs += __popc(mp);
-            emit_m2l_pairs(a, lane, lt_mask, emit_m, (unsigned)leaf, jme[u]);
         }
+        const unsigned m2 = __ballot_sync(0xffffffffu, npush == 2);
+        const int pos0 = sbase + 2 * __popc(m2 & lt_mask);
+        const int top = sbase + 2 * __popc(m2);
+        if (top > STACK_CAP) { err = 1; return false; }
+        if (npush == 2) { stack[pos0] = p0; stack[pos0 + 1] = p1; }
+        const unsigned mp = __ballot_sync(0xffffffffu, emit_p);
+        if (emit_p) queue[(qtail + __popc(mp & lt_mask)) & (QCAP - 1)] = ent;
+        qtail += __popc(mp);
+        npairs += __popc(mp);
+        emit_m2l_pairs(a, lane, lt_mask, emit_m, (unsigned)leaf, jme);
         ssize = top;
         __syncwarp();
         return true;
@@ -415,7 +405,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32) walk_leaf_kernel(WalkArgs a, 
     const int leaf = blockIdx.x * WALK_WARPS + wib;
     if (leaf >= a.nleaf) return;
     const int q = lane / SW, j = lane % SW;
-    LeafWalk<MODE, 1, SRCQ_CAP> w;
+    LeafWalk<MODE, SRCQ_CAP> w;
     w.begin(a, leaf, s_stack[wib], s_srcq[wib], s_sink[wib], lane);
     const LeafDesc sd = w.sd;
     double xd = 0, yd = 0, zd = 0, axd = 0, ayd = 0, azd = 0;
@@ -513,7 +503,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, LEAF_MIN_BLOCKS) walk_fused_k
     const int leaf = blockIdx.x * WALK_WARPS + wib;
     if (leaf >= a.nleaf) return;
     const int q = lane / SW, j = lane % SW;
-    LeafWalk<0, 1, SRCQ_CAP> w;
+    LeafWalk<0, SRCQ_CAP> w;
     w.begin(a, leaf, s_stack[wib], s_srcq[wib], s_sink[wib], lane);
     // sink: slot j of the leaf's own tile (padding slots compute, but are never written)
     float xi, yi, zi;
