@@ -193,6 +193,18 @@ int pn2_migrate_result(pn2_ctx *h, double **d_rec_out, int *n_out, int *recvcoun
 int pn2_migrate_fetch(pn2_ctx *h, double *rec_host_out);
 int pn2_migrate_device(pn2_ctx *h, const double *d_rec, int rec_doubles, int n, const double *split, double **d_rec_out, int *n_out);
 
+/* ---- KDK integrator on the device (src/photoNs.c:150-196, 254-268) ---------------------------------
+ * Operates on device arrays of the reference's Body records (12 doubles: pos 0-2, acc 3-5, vel 6-8, acc_pm 9-11,
+ * inc/typesdef.h:25-31).  The factors come from the host (kick_loga / drift_loga, src/initial.c:639-683:
+ * photons-2.0_b200/cosmology.py): dkh = 0.5 * kick * GravConst, dd = drift.
+ *   pn2_kick_device : vel += a1 * dkh; vel += a2 * dkh -- two separately rounded updates in the reference's order:
+ *                     pm_first != 0: a1 = acc_pm, a2 = acc (opening half kick, :158-169); else a1 = acc, a2 = acc_pm
+ *                     (closing half kick, :257-268).
+ *   pn2_drift_device: pos += vel * dd, then wrapped into [0, box) by repeated +/- box (:171-196).
+ * Results are bit-identical to the reference's loops (no FMA contraction). */
+int pn2_kick_device(pn2_ctx *h, double *d_body, int n, double dkh, int pm_first);
+int pn2_drift_device(pn2_ctx *h, double *d_body, int n, double dd, double box);
+
 /* ---- Mode B inspection (tests: bit-exact tree / list checks; not needed by the product path) --- */
 typedef struct {
     int32_t n, nleaf, nnode, nlevel;

@@ -34,7 +34,7 @@ EXPORTS = ["pn2_create", "pn2_destroy", "pn2_set_params", "pn2_sync", "pn2_last_
            "pn2_get_timings", "pn2_launch_count", "pn2_timer_start", "pn2_timer_stop", "pn2_comm_unique_id",
            "pn2_comm_init_rank", "pn2_step_begin", "pn2_exchange_local", "pn2_step_finish", "pn2_domain_owner_device",
            "pn2_migrate_begin", "pn2_migrate_exchange_nccl", "pn2_migrate_exchange_local", "pn2_migrate_result",
-           "pn2_migrate_device", "pn2_migrate_fetch"]
+           "pn2_migrate_device", "pn2_migrate_fetch", "pn2_kick_device", "pn2_drift_device"]
 
 
 class Pn2Error(RuntimeError):
@@ -138,6 +138,8 @@ def lib():
     L.pn2_migrate_result.argtypes = [vp, C.POINTER(vp), ip, vp]
     L.pn2_migrate_device.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.POINTER(vp), ip]
     L.pn2_migrate_fetch.argtypes = [vp, vp]
+    L.pn2_kick_device.argtypes = [vp, vp, C.c_int, C.c_double, C.c_int]
+    L.pn2_drift_device.argtypes = [vp, vp, C.c_int, C.c_double, C.c_double]
     L.pn2_timer_start.argtypes = [vp, C.c_int]
     L.pn2_timer_stop.argtypes = [vp, C.c_int, dp]
     L.pn2_launch_count.argtypes = [vp]
@@ -354,6 +356,13 @@ class Context:
         self.migrate_exchange_nccl()
         ptr, n_new, _ = self.migrate_result()
         return ptr, n_new
+
+    # ---- KDK integrator on device Body records (src/photoNs.c:150-196, 254-268) ----
+    def kick_device(self, d_body_ptr, n, dkh, pm_first):
+        _ck(lib().pn2_kick_device(self.h, d_body_ptr, n, dkh, 1 if pm_first else 0))
+
+    def drift_device(self, d_body_ptr, n, dd, box):
+        _ck(lib().pn2_drift_device(self.h, d_body_ptr, n, dd, box))
 
     def step_info(self):
         s = StepInfo()
