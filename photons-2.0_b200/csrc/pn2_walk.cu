@@ -40,13 +40,12 @@ struct WalkArgs {
     const int *son;
     const LeafDesc *desc;
     const int *parent;
-    const float4 *rel;
     const float *tiles;                // FP32 mode: leaf tiles (see walk_fused_kernel), pad_tile = the all-padding tile
     int pad_tile;
     const double *pos;
     double *acc;
     double cutoff, theta;
-    int longshort, nimg, maxleaf;
+    int longshort;
     double tc[3], tw[3];               // this rank's domain box (pruning target for image trees)
     // span lists: 16-byte units; span = {count, next, 0, 0} + entries
     unsigned *spans;
@@ -629,9 +628,8 @@ static void fill_args(pn2_ctx *h, WalkArgs &a) {
     a.nleaf = h->nleaf; a.ncell = h->ncell; a.root = h->nleaf;
     a.rleaf0 = h->ncell; a.rnode0 = h->ncell + h->nrl; a.root_head = h->root_head;
     a.geom = h->geom.p; a.son = h->son.p; a.desc = h->desc.p; a.parent = h->parent.p;
-    a.rel = h->rel.p; a.pos = h->pos.p; a.acc = h->acc.p;
-    a.cutoff = h->prm.cutoff; a.theta = h->prm.theta; a.longshort = h->prm.longshort; a.maxleaf = h->prm.maxleaf;
-    a.nimg = h->prm.periodic ? 27 : 1;
+    a.pos = h->pos.p; a.acc = h->acc.p;
+    a.cutoff = h->prm.cutoff; a.theta = h->prm.theta; a.longshort = h->prm.longshort;
     for (int d = 0; d < 3; d++) {
         // the pruning box of prepare_sendtree2 is the target's box as centre / width (src/remotes.c:97-110)
         a.tc[d] = 0.5 * (h->dom.hi[d] + h->dom.lo[d]);
