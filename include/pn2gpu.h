@@ -205,6 +205,12 @@ int pn2_migrate_device(pn2_ctx *h, const double *d_rec, int rec_doubles, int n, 
 int pn2_kick_device(pn2_ctx *h, double *d_body, int n, double dkh, int pm_first);
 int pn2_drift_device(pn2_ctx *h, double *d_body, int n, double dd, double box);
 
+/* The Mode B force step on device-resident RECORDS (first three doubles = position, e.g. the reference's Body): the
+ * short-range accelerations are written to doubles acc_offset .. acc_offset + 2 of every record (Body.acc: 3), so that
+ * force -> kick -> drift -> migrate runs without a host copy of the particles (src/photoNs.c:97-116, 150-196).
+ * Same result as pn2_force_step_device on the packed positions. */
+int pn2_force_step_records(pn2_ctx *h, double *d_rec, int rec_doubles, int acc_offset, int n, const pn2_domain *dom);
+
 /* ---- Mode B inspection (tests: bit-exact tree / list checks; not needed by the product path) --- */
 typedef struct {
     int32_t n, nleaf, nnode, nlevel;

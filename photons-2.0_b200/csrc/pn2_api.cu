@@ -88,7 +88,7 @@ extern "C" int pn2_destroy(pn2_ctx *h) {
     if (!h) return PN2_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    h->pos.release(); h->acc.release(); h->rel.release(); h->tiles.release(); h->geom.release(); h->son.release(); h->desc.release();
+    h->pos.release(); h->acc.release(); h->rel.release(); h->tiles.release(); h->rec_pos.release(); h->rec_acc.release(); h->geom.release(); h->son.release(); h->desc.release();
     h->M.release(); h->L.release(); h->level_nodes.release(); h->r_desc.release(); h->r_geom.release();
     h->r_M.release(); h->r_pos.release(); h->r_rel.release(); h->ia.release(); h->ib.release(); h->ic.release();
     h->id_.release(); h->la.release(); h->ua.release(); h->ub.release(); h->tmp.release(); h->counters.release();

@@ -156,6 +156,7 @@ struct pn2_ctx {
     bool own_comm = false;
     struct LetState *let = nullptr;
     struct MigState *mig = nullptr;     // domain decomposition (pn2_migrate.cu)
+    DBuf<double> rec_pos, rec_acc;      // packed positions / accelerations of pn2_force_step_records
     std::vector<pn2_domain> all_dom;
     void *nccl = nullptr;
     cudaEvent_t ev[10] = {nullptr};

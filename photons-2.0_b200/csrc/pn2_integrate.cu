@@ -52,3 +52,38 @@ extern "C" int pn2_drift_device(pn2_ctx *h, double *d_body, int n, double dd, do
     KERNEL_CHECK();
     return PN2_OK;
 }
+
+// ---- force step on records: positions gathered from / accelerations scattered to the strided records ----
+__global__ void gather_pos_kernel(long total, const double *__restrict__ rec, int rd, double *__restrict__ pos) {
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const long i = t / 3;
+    pos[t] = rec[(size_t)i * rd + (t - 3 * i)];
+}
+__global__ void scatter_acc_records_kernel(long total, const double *__restrict__ acc, double *__restrict__ rec, int rd, int off) {
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const long i = t / 3;
+    rec[(size_t)i * rd + off + (t - 3 * i)] = acc[t];
+}
+
+extern "C" int pn2_force_step_records(pn2_ctx *h, double *d_rec, int rec_doubles, int acc_offset, int n, const pn2_domain *dom) {
+    if (!h || n < 0 || (n > 0 && !d_rec) || rec_doubles < 6 || acc_offset < 3 || acc_offset + 3 > rec_doubles) {
+        pn2_set_error("pn2_force_step_records: bad argument");
+        return PN2_ERR_ARG;
+    }
+    CUDA_TRY(cudaSetDevice(h->device));
+    PN2_TRY(h->rec_pos.ensure(3 * (size_t)n + 3)); PN2_TRY(h->rec_acc.ensure(3 * (size_t)n + 3));
+    const long total = 3L * n;
+    if (n > 0) {
+        gather_pos_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(total, d_rec, rec_doubles, h->rec_pos.p);
+        h->launches++;
+    }
+    PN2_TRY(pn2_force_step_device(h, h->rec_pos.p, n, dom, h->rec_acc.p));
+    if (n > 0) {
+        scatter_acc_records_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(total, h->rec_acc.p, d_rec, rec_doubles, acc_offset);
+        h->launches++;
+    }
+    KERNEL_CHECK();
+    return PN2_OK;
+}

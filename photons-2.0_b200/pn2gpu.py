@@ -34,7 +34,7 @@ EXPORTS = ["pn2_create", "pn2_destroy", "pn2_set_params", "pn2_sync", "pn2_last_
            "pn2_get_timings", "pn2_launch_count", "pn2_timer_start", "pn2_timer_stop", "pn2_comm_unique_id",
            "pn2_comm_init_rank", "pn2_step_begin", "pn2_exchange_local", "pn2_step_finish", "pn2_domain_owner_device",
            "pn2_migrate_begin", "pn2_migrate_exchange_nccl", "pn2_migrate_exchange_local", "pn2_migrate_result",
-           "pn2_migrate_device", "pn2_migrate_fetch", "pn2_kick_device", "pn2_drift_device"]
+           "pn2_migrate_device", "pn2_migrate_fetch", "pn2_kick_device", "pn2_drift_device", "pn2_force_step_records"]
 
 
 class Pn2Error(RuntimeError):
@@ -140,6 +140,7 @@ def lib():
     L.pn2_migrate_fetch.argtypes = [vp, vp]
     L.pn2_kick_device.argtypes = [vp, vp, C.c_int, C.c_double, C.c_int]
     L.pn2_drift_device.argtypes = [vp, vp, C.c_int, C.c_double, C.c_double]
+    L.pn2_force_step_records.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(Domain)]
     L.pn2_timer_start.argtypes = [vp, C.c_int]
     L.pn2_timer_stop.argtypes = [vp, C.c_int, dp]
     L.pn2_launch_count.argtypes = [vp]
@@ -363,6 +364,14 @@ class Context:
 
     def drift_device(self, d_body_ptr, n, dd, box):
         _ck(lib().pn2_drift_device(self.h, d_body_ptr, n, dd, box))
+
+    def force_step_records(self, d_rec_ptr, rec_doubles, n, domain=None, acc_offset=3):
+        """Mode B force step on device records; accelerations go to doubles acc_offset.. of every record (Body.acc)."""
+        if domain is None:
+            b = self.params.box
+            domain = make_domain([0, 0, 0], [b, b, b], 0)
+        _ck(lib().pn2_force_step_records(self.h, d_rec_ptr, rec_doubles, acc_offset, n, C.byref(domain)))
+        self.n = n
 
     def step_info(self):
         s = StepInfo()
