@@ -33,6 +33,9 @@ CASES = [
     (4, [[1.2, 0.8, 1.1, 0.9], [0.7, 1.4, 1.0, 0.9]]),
     (5, [[1.6, 0.8, 0.9, 0.7, 1.0], [1.1, 1.0, 0.9, 1.2, 0.8]]),
     (8, [[1.4, 0.6, 1.1, 0.9, 1.3, 0.7, 1.0, 1.0], [0.9, 1.1, 1.0, 1.2, 0.8, 1.0, 0.9, 1.1], [1.0] * 8]),
+    (6, [[1.3, 0.7, 1.1, 0.9, 1.2, 0.8], [0.9, 1.0, 1.1, 1.0, 0.8, 1.2]]),
+    (7, [[0.6, 1.4, 1.0, 1.1, 0.9, 1.2, 0.8], [1.0] * 7]),
+    (16, [[1.0 + 0.05 * ((3 * k) % 7 - 3) for k in range(16)], [1.0 + 0.04 * ((5 * k) % 9 - 4) for k in range(16)]]),
 ]
 
 
