@@ -90,3 +90,50 @@ def test_adaptive_splits_match_reference_golden():
             for r in range(P):
                 q = pos[own == r]
                 assert np.all(q >= np.array(doms[r].lo)) and np.all(q <= np.array(doms[r].hi))
+
+
+def test_gloo_two_ranks_adaptive_decomposition():
+    """world_size 2 over gloo: the per-step decomposition loop of src/photoNs.c:277-283 + src/domains.c:384-394 --
+    every rank reports its load (here: its particle count, standing in for idxP2P + idxM2L), the loads are gathered
+    (MPI_Allgather in measure_domain_runtime), every rank updates the same DomainTree, particles change owner; the
+    ranks must agree on the splits bit for bit, the set stays partitioned, and the imbalance shrinks."""
+    code = r'''
+import os, sys
+sys.path.insert(0, os.path.join(ROOT, "photons-2.0_b200"))
+import torch, torch.distributed as dist
+import numpy as np
+import domains
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+pos = np.load(os.path.join(ROOT, "tests", "golden", "demo_pos_f32.npy")).astype(np.float64)      # clustered demo IC
+dt = domains.DomainTree(world, 100000.0)
+imb = []
+for step in range(6):
+    own = dt.owner(pos)
+    mine = int((own == rank).sum())
+    cnt = torch.tensor([float(mine)], dtype=torch.float64)
+    allc = [torch.zeros(1, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(allc, cnt)
+    counts = np.array([float(c) for c in allc])
+    assert counts.sum() == len(pos)
+    imb.append(counts.max() / counts.mean())
+    load = counts * world / (counts.sum() + 0.0001)               # DTIME_FRACTION, src/photoNs.c:283
+    dt.update(load)
+    s = torch.from_numpy(dt.splits.copy())
+    ref = s.clone()
+    dist.broadcast(ref, 0)
+    assert torch.equal(s, ref)                                     # same doubles on every rank
+    lo, hi = np.array(dt.boxes()[rank].lo), np.array(dt.boxes()[rank].hi)
+    q = pos[dt.owner(pos) == rank]
+    assert bool(((q >= lo) & (q <= hi)).all())
+assert imb[-1] < imb[0] or imb[0] < 1.001, imb
+dist.destroy_process_group()
+print("ok", rank, ["%.4f" % x for x in imb])
+'''.replace("ROOT", repr(ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29614")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29614", "--no-python", sys.executable, "-c", code],
+                       env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("ok") == 2
+    print(r.stdout[-300:])
