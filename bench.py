@@ -164,7 +164,7 @@ def run_reference_arm(args):
     out = {"metric": METRIC, "value": pps, "unit": "particles/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
            "data": "synthetic", "impl": "reference",
-           "config": workload_config(args, 1) | {"reference_sample": sample},
+           "config": workload_config(args, args.gpus) | {"reference_sample": sample},
            "p2p_ginteractions_per_s": r["interactions_per_particle"] * pps / 1e9,
            "cpu_baseline": {"value": pps, "unit": "particles/s", "cores": r["cores"], "kind": r["kind"], "sample": sample},
            "e2e": {"value": pps, "unit": "particles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
