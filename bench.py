@@ -107,7 +107,7 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def reference_cpu_run(args, side, nranks, repeat=1):
+def reference_cpu_run(args, side, nranks, repeat=1, keep=False):
     """The reference's own CPU implementation of the path (oracle/_ref/ref_fmm: the UNMODIFIED reference
     sources with a fork/socketpair MPI shim, PM excluded) on a bounded sample of the workload: the same
     generator at side^3 particles with NSIDE = side * (nside / npart_side), i.e. the same interactions per
@@ -130,6 +130,9 @@ def reference_cpu_run(args, side, nranks, repeat=1):
         nint = sum(r["nint_local"] + r["p2p_count_remote"] for r in ranks)
         if not (sec > 0):
             sec = wall / max(1, repeat)
+        if keep:           # the sample's positions and the reference's accelerations, for the parity block of the bench line
+            kept = {"pos": pos, "acc": pn_ref.gather_acc(ranks, n), "nleaf": [r["last_leaf"] - r["first_leaf"] for r in ranks],
+                    "nint": [r["nint_local"] + r["p2p_count_remote"] for r in ranks], "mass": mass}
     else:
         kind = "port"
         prm = pn_oracle.make_params(synthetic.BOX, nside_pm, n, mass, maxleaf=args.maxleaf, theta=args.theta)
@@ -138,8 +141,44 @@ def reference_cpu_run(args, side, nranks, repeat=1):
         sec = time.perf_counter() - t0
         nint = cnt["int_local"] + cnt["int_remote"]
         nranks = 1
-    return {"pps": n / sec, "ips": nint / sec, "sec": sec, "kind": kind, "cores": nranks, "n": n, "side": side,
-            "nside": nside_pm, "interactions_per_particle": nint / n}
+    out = {"pps": n / sec, "ips": nint / sec, "sec": sec, "kind": kind, "cores": nranks, "n": n, "side": side,
+           "nside": nside_pm, "interactions_per_particle": nint / n}
+    if keep and kind == "reference":
+        out["kept"] = kept
+    return out
+
+
+def parity_vs_reference(args, r):
+    """The product path against the UNMODIFIED reference on the CPU-baseline sample of this very run: Mode B in both
+    arithmetic modes at the reference's rank count (one context per rank on this GPU, LET blocks exchanged
+    device-to-device by pn2_exchange_local: same domain rule, src/domains.c:399-428), accelerations compared with
+    the ones the reference harness computed (rms relative error, north_star: <= 1e-6 FP64, <= 1e-4 FP32), leaf
+    and interaction counts compared rank by rank."""
+    import pn2gpu
+    import domains
+    import synthetic
+    k = r["kept"]
+    pos, ref, nr = k["pos"], k["acc"], r["cores"]
+    doms = domains.domain_boxes(nr, synthetic.BOX)
+    owner = domains.domain_of(pos, nr, synthetic.BOX)
+    idx = [np.nonzero(owner == q)[0] for q in range(nr)]
+    out = {"sample": f"{r['side']}^3 particles, NSIDE {r['nside']}, {nr} ranks (the cpu_baseline run of this line)",
+           "reference": "oracle/_ref/ref_fmm (unmodified reference sources)", "tolerance": {"fp64_rms": 1e-6, "fp32_rms": 1e-4}}
+    for name, precision in (("fp64", pn2gpu.FP64), ("fp32", pn2gpu.FP32)):
+        prm = pn2gpu.make_params(synthetic.BOX, r["nside"], len(pos), k["mass"], maxleaf=args.maxleaf, theta=args.theta, precision=precision)
+        ctxs = [pn2gpu.Context(prm) for _ in range(nr)]
+        accs = pn2gpu.force_step_local_ranks(ctxs, [pos[i] for i in idx], doms)
+        acc = np.zeros_like(pos)
+        for q in range(nr):
+            acc[idx[q]] = accs[q]
+        infos = [c.step_info() for c in ctxs]
+        for c in ctxs:
+            c.close()
+        out[name + "_rms"] = float(np.sqrt(((acc - ref) ** 2).sum() / (ref ** 2).sum()))
+        out["nleaf_equal"] = bool(out.get("nleaf_equal", True) and [i["nleaf"] for i in infos] == [int(x) for x in k["nleaf"]])
+        out["nint_equal"] = bool(out.get("nint_equal", True) and [i["n_interactions"] for i in infos] == [int(x) for x in k["nint"]])
+    out["pass"] = bool(out["fp64_rms"] <= 1e-6 and out["fp32_rms"] <= 1e-4 and out["nleaf_equal"] and out["nint_equal"])
+    return out
 
 
 def run_reference_arm(args):
@@ -164,7 +203,12 @@ def run_reference_arm(args):
     out = {"metric": METRIC, "value": pps, "unit": "particles/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
            "data": "synthetic", "impl": "reference",
-           "config": workload_config(args, args.gpus) | {"reference_sample": sample},
+           "config": workload_config(args, args.gpus) | {
+               "workload": f"bounded sample of the arm's workload: synthetic LCDM-like {side}^3 particles (same generator, seed), NSIDE {r['nside']}, "
+                           f"Zel'dovich displacement rms {args.disp_rms} grid spacings",
+               "npart": r["n"], "nside": r["nside"], "parallelism": f"mpi_shim_ranks{r['cores']}", "precision_mode": "fp64 (the reference's arithmetic)",
+               "sample_of": f"{args.npart_side}^3 particles, NSIDE {args.nside or args.npart_side} (the GPU arm's workload; same interactions per particle)",
+               "cache": "n/a (host)", "reference_sample": sample},
            "p2p_ginteractions_per_s": r["interactions_per_particle"] * pps / 1e9,
            "cpu_baseline": {"value": pps, "unit": "particles/s", "cores": r["cores"], "kind": r["kind"], "sample": sample},
            "e2e": {"value": pps, "unit": "particles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -295,6 +339,11 @@ def main():
     else:
         ms_total, nint_total, n_total, walk_ms = [float(x) for x in t]
     ms_step = ms_total / args.steps
+    # Newton's third law over the whole periodic set: |sum a| / sum |a| (all ranks), a size-independent property check
+    mom = torch.cat([acc.sum(0), torch.linalg.vector_norm(acc, dim=1).sum().reshape(1)])
+    if world > 1:
+        dist.all_reduce(mom, op=dist.ReduceOp.SUM)
+    momentum_residual = float(torch.linalg.vector_norm(mom[:3]) / mom[3])
 
     # ---- e2e: the same step through the host-pointer C-ABI call: pinned host positions in, accelerations out ----
     e2e = None
@@ -318,9 +367,12 @@ def main():
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e_ms = float(te[0]) / args.steps
+        m_chk = min(n, 1 << 22)
         e2e = {"value": n_total / (e_ms * 1e-3), "unit": "particles/s", "h2d_bytes_per_step": int(n_total) * 24,
                "d2h_bytes_per_step": int(n_total) * 24, "ms_per_step": e_ms,
-               "check_rms_acc": float(torch.sqrt((hacc[: min(n, 1 << 20)] ** 2).sum(1).mean()))}
+               # the host-pointer call must return what the device-resident step computed (same deterministic kernels)
+               "max_abs_diff_vs_device_step_rank0": float((hacc[:m_chk].to(dev) - acc[:m_chk]).abs().max()),
+               "rms_acc_rank0": float(torch.sqrt((acc[:m_chk] ** 2).sum(1).mean()))}
 
     if rank != 0:
         if world > 1:
@@ -349,7 +401,7 @@ def main():
            "config": workload_config(args, world),
            "p2p_ginteractions_per_s": nint_total / (ms_step * 1e-3) / 1e9,
            "interactions_per_particle": nint_total / n_total,
-           "migrate": migrate,
+           "migrate": migrate, "momentum_residual": momentum_residual,
            "phases_ms": {k: float(np.mean([p[k] for p in phase])) for k in ("tree", "upward", "frontier", "walk_p2p", "m2l", "downward", "let", "total")},
            "tree": {"nleaf": info["nleaf"], "nnode": info["nnode"], "levels": info["nlevel"], "m2l_pairs": info["n_m2l_pairs"],
                     "p2p_leaf_pairs": info["n_p2p_pairs"], "walk_visits": info["n_walk_visits"],
@@ -367,12 +419,17 @@ def main():
         while nr * 2 <= cores:
             nr *= 2
         try:
-            r = reference_cpu_run(args, args.cpu_sample_side, nr)
+            r = reference_cpu_run(args, args.cpu_sample_side, nr, keep=True)
             out["cpu_baseline"] = {"value": r["pps"], "unit": "particles/s", "cores": r["cores"], "kind": r["kind"],
                                    "sample": f"{r['side']}^3 particles of the same generator, NSIDE {r['nside']}, one force evaluation, "
                                              f"NP={r['cores']} ranks of the unmodified reference (PM excluded), "
                                              f"{r['interactions_per_particle']:.0f} interactions/particle, {r['sec']:.1f} s",
                                    "p2p_ginteractions_per_s": r["ips"] / 1e9}
+            if "kept" in r:
+                try:
+                    out["parity"] = parity_vs_reference(args, r)
+                except Exception as ex:
+                    out["parity"] = {"pass": False, "error": repr(ex)[:300]}
         except Exception as ex:  # the bench line must still be printed
             out["cpu_baseline"] = {"value": None, "unit": "particles/s", "cores": cores, "kind": "unavailable", "sample": repr(ex)[:300]}
     print(json.dumps(out), file=_OUT, flush=True)

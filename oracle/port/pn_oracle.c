@@ -2,7 +2,7 @@
  * pn_oracle.c -- CPU restatement ("port") of photoNs-2.0's short-range FMM path.
  *
  * TEST INFRASTRUCTURE ONLY (see pn_oracle.h).  PARITY PINNED against the unmodified reference
- * (oracle/_ref) in tests/test_oracle_vs_ref.py and against tests/golden/.
+ * (oracle/_ref) in tests/test_oracle_golden.py and against tests/golden/.
  *
  * Every function cites the reference lines it restates.  Geometry, tree construction and the
  * acceptance test reproduce the reference's floating-point expression ORDER (they decide tree

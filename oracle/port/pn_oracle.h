@@ -5,7 +5,7 @@
  * linked into, imported by, or executed from the product (only tests/, __graft_entry__.smoke()
  * and bench.py's cpu_baseline / --impl reference legs may use it).
  *
- * PARITY PINNED: every function below is checked in tests/test_oracle_vs_ref.py against the
+ * PARITY PINNED: every function below is checked in tests/test_oracle_golden.py against the
  * unmodified reference compiled from /root/reference (oracle/_ref) and against fixtures in
  * tests/golden/ generated from it (tests/golden/make_golden.py).
  *

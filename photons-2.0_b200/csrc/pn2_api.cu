@@ -350,6 +350,7 @@ int pn2_build_csr(pn2_ctx *h, const int *h_s, const int *h_t, long n, int remote
 int pn2_csr_from_device_pairs(pn2_ctx *h, int *tcell, unsigned *scell, long n, CsrList *out) {
     out->nseg = 0;
     if (n == 0) return PN2_OK;
+    if (n < 0 || n >= (1L << 31) - 1) { pn2_set_error("pn2: %ld list pairs in one CSR build (limit 2^31 - 2)", n); return PN2_ERR_ARG; }
     cudaStream_t st = h->stream;
     PN2_TRY(h->ia.ensure(n)); PN2_TRY(h->ib.ensure(n + 1)); PN2_TRY(h->ic.ensure(n + 1));
     PN2_TRY(h->ub.ensure(n)); PN2_TRY(h->la.ensure(n + 2)); PN2_TRY(h->b_scal.ensure(16));

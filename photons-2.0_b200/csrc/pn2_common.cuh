@@ -157,6 +157,7 @@ struct pn2_ctx {
     struct LetState *let = nullptr;
     struct MigState *mig = nullptr;     // domain decomposition (pn2_migrate.cu)
     DBuf<double> rec_pos, rec_acc;      // packed positions / accelerations of pn2_force_step_records
+    DBuf<double> stage_in, stage_out;   // device staging of pn2_force_step's host positions / accelerations
     std::vector<pn2_domain> all_dom;
     void *nccl = nullptr;
     cudaEvent_t ev[10] = {nullptr};

@@ -10,7 +10,7 @@ void pn2_modeb_release(pn2_ctx *h) {
     h->b_seg.release(); h->b_seg2.release(); h->b_q.release(); h->b_key2.release(); h->b_f.release(); h->b_flag.release();
     h->n_start.release(); h->n_count.release(); h->n_son.release(); h->n_depth.release(); h->l_start.release();
     h->l_count.release(); h->n_box.release(); h->n_split.release(); h->l_box.release(); h->b_cnt.release();
-    h->b_scal.release(); h->m2l_pairs.release(); h->spans.release(); h->o_head.release(); h->lst_off.release(); h->lst_src.release(); h->lst_sink.release();
+    h->b_scal.release(); h->stage_in.release(); h->stage_out.release(); h->m2l_pairs.release(); h->spans.release(); h->o_head.release(); h->lst_off.release(); h->lst_src.release(); h->lst_sink.release();
     for (int i = 0; i < 10; i++) if (h->ev[i]) { cudaEventDestroy(h->ev[i]); h->ev[i] = nullptr; }
     pn2_let_release(h);
     pn2_migrate_release(h);
@@ -43,6 +43,15 @@ extern "C" int pn2_step_begin(pn2_ctx *h, const double *d_pos, int n, const pn2_
     for (int d = 0; d < 3; d++)
         if (!(dom->hi[d] > dom->lo[d])) { pn2_set_error("pn2_step_begin: empty domain box"); return PN2_ERR_ARG; }
     if (dom->direct0 < 0 || dom->direct0 > 2) { pn2_set_error("pn2_step_begin: direct0 must be 0..2"); return PN2_ERR_ARG; }
+    if (h->nranks > 1) {
+        // the LET receiver re-derives the sender's prune decisions from ITS box (pruned_dev, pn2_walk.cu): the box of this
+        // step must be the one the peers were given for this rank (pn2_set_comm / pn2_comm_init_rank)
+        if ((int)h->all_dom.size() != h->nranks) { pn2_set_error("pn2_step_begin: no domain table (pn2_set_comm)"); return PN2_ERR_STATE; }
+        const pn2_domain &me = h->all_dom[h->rank];
+        bool same = me.direct0 == dom->direct0;
+        for (int d = 0; d < 3; d++) same = same && me.lo[d] == dom->lo[d] && me.hi[d] == dom->hi[d];
+        if (!same) { pn2_set_error("pn2_step_begin: dom differs from all_domains[rank] of pn2_set_comm (stale domain table?)"); return PN2_ERR_ARG; }
+    }
     CUDA_TRY(cudaSetDevice(h->device));
     PN2_TRY(ensure_events(h));
     cudaStream_t st = h->stream;
@@ -102,6 +111,10 @@ extern "C" int pn2_step_finish(pn2_ctx *h, double *d_acc) {
         CUDA_TRY(cudaMemcpyAsync(cnt, h->counters.p, sizeof cnt, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
         if (cnt[3] & 1) { pn2_set_error("pn2: walk stack overflow (pathological particle distribution)"); return PN2_ERR_NOMEM; }
+        if (cnt[3] & 4) {
+            pn2_set_error("pn2: a leaf is wider than 9.8 lambda = 13.6 rs: the FP32 tile layout of the long/short split cannot hold it; use PN2_FP64");
+            return PN2_ERR_ARG;
+        }
         bool redo = false;
         if (cnt[3] & 2) {                                              // span buffer too small
             // a pass that ran out of room truncates the deeper levels' lists, so cnt[6] can underestimate the need:
@@ -163,7 +176,7 @@ extern "C" int pn2_force_step(pn2_ctx *h, const double *pos, size_t pos_stride, 
         return PN2_ERR_ARG;
     }
     CUDA_TRY(cudaSetDevice(h->device));
-    static thread_local DBuf<double> in, out;
+    DBuf<double> &in = h->stage_in, &out = h->stage_out;      // owned by the context: right device, freed by pn2_destroy
     PN2_TRY(in.ensure(3 * (size_t)n + 3)); PN2_TRY(out.ensure(3 * (size_t)n + 3));
     if (n > 0) {
         if (pos_stride == 24) CUDA_TRY(cudaMemcpyAsync(in.p, pos, 24 * (size_t)n, cudaMemcpyHostToDevice, h->stream));

@@ -320,8 +320,10 @@ __global__ void finalize_cells_kernel(int nleaf, int nnode, const int *__restric
     desc[c] = d;
 }
 
-int pn2_tree_build_device(pn2_ctx *h, const double *d_pos_in, int n, const pn2_domain *dom) {
+// one attempt with room for `cap` leaves and `cap` nodes; *overflow is set when that was not enough
+static int tree_build_once(pn2_ctx *h, const double *d_pos_in, int n, const pn2_domain *dom, int cap, bool *overflow) {
     cudaStream_t st = h->stream;
+    *overflow = false;
     const int maxleaf = h->prm.maxleaf;
     h->n = n;
     h->dom = *dom;
@@ -332,14 +334,11 @@ int pn2_tree_build_device(pn2_ctx *h, const double *d_pos_in, int n, const pn2_d
     PN2_TRY(h->acc.ensure(3 * (size_t)n + 3)); PN2_TRY(h->rel.ensure((size_t)n + 1));
     PN2_TRY(h->order.ensure(n + 1)); PN2_TRY(h->b_idx2.ensure(n + 1));
     PN2_TRY(h->b_seg.ensure(n + 1)); PN2_TRY(h->b_seg2.ensure(n + 1));
-    PN2_TRY(h->b_q.ensure(n + 2)); PN2_TRY(h->b_key2.ensure(n + 2)); PN2_TRY(h->b_f.ensure(n + 2)); PN2_TRY(h->b_flag.ensure((size_t)n + 16));
+    PN2_TRY(h->b_q.ensure((size_t)(n > cap ? n : cap) + 2)); PN2_TRY(h->b_key2.ensure(n + 2)); PN2_TRY(h->b_f.ensure(n + 2)); PN2_TRY(h->b_flag.ensure((size_t)n + 16));
     PN2_TRY(h->b_pay.ensure((size_t)n + 1)); PN2_TRY(h->b_pay2.ensure((size_t)n + 1));
     PN2_TRY(h->b_qc.ensure((size_t)n + 1)); PN2_TRY(h->b_qc2.ensure((size_t)n + 1));
     PN2_TRY(h->b_scal.ensure(16));
     if (n == 0) return PN2_OK;
-    // capacities: a full binary tree, nnode = nleaf - 1; leaves hold >= 1 particle unless coordinates coincide
-    int cap = n / 2 + 1024;
-    if (cap > n + 2) cap = n + 2;
     PN2_TRY(h->n_start.ensure(cap)); PN2_TRY(h->n_count.ensure(cap)); PN2_TRY(h->n_son.ensure(2 * (size_t)cap));
     PN2_TRY(h->n_depth.ensure(cap)); PN2_TRY(h->n_box.ensure(6 * (size_t)cap)); PN2_TRY(h->n_split.ensure(cap));
     PN2_TRY(h->n_sum.ensure(cap));
@@ -407,7 +406,7 @@ int pn2_tree_build_device(pn2_ctx *h, const double *d_pos_in, int n, const pn2_d
         int hs[4];
         CUDA_TRY(cudaMemcpyAsync(hs, h->b_scal.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
-        if (hs[3]) { pn2_set_error("pn2: tree capacity %d exceeded (degenerate particle distribution)", cap); return PN2_ERR_NOMEM; }
+        if (hs[3]) { *overflow = true; return PN2_OK; }
         std::swap(pc, po); std::swap(qc, qo); std::swap(sg, so);
         node0 += cnt;
         level_off.push_back(node0);
@@ -436,4 +435,22 @@ int pn2_tree_build_device(pn2_ctx *h, const double *d_pos_in, int n, const pn2_d
     h->have_particles = true;
     h->have_tree = true;
     return PN2_OK;
+}
+
+// Capacity of the leaf / node records: the reference sizes NLEAF = NNODE = 2 NPART / MAXLEAF (src/fmm.c:203-204,
+// unchecked); mean splits that peel off single particles (or MAXLEAF 1..2) need more, so an attempt that runs out of
+// room is repeated with twice the capacity (a full binary tree over n distinct particles has < n leaves; empty leaves
+// appear only where all coordinates of a node coincide in the split direction).
+int pn2_tree_build_device(pn2_ctx *h, const double *d_pos_in, int n, const pn2_domain *dom) {
+    long cap = 2L * n / h->prm.maxleaf + 1024;
+    if (cap < (long)n / 2 + 1024) cap = (long)n / 2 + 1024;
+    const long cap_max = 4L * n + 1024;
+    for (;;) {
+        if (cap > cap_max) cap = cap_max;
+        bool overflow = false;
+        PN2_TRY(tree_build_once(h, d_pos_in, n, dom, (int)cap, &overflow));
+        if (!overflow) return PN2_OK;
+        if (cap >= cap_max) { pn2_set_error("pn2: tree capacity %ld exceeded (degenerate particle distribution)", cap); return PN2_ERR_NOMEM; }
+        cap *= 2;
+    }
 }

@@ -234,7 +234,8 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NODE_MIN_BLOCKS) frontier_nod
             } else {
                 int pruned = 0;
                 if (remote) {
-                    if (!lj) pruned = pruned_dev(cj, wj, pc.shift[img], a.tc, a.tw, a.cutoff, a.theta, a.longshort);
+                    // a packed node whose sons were not sent (-1) is terminal whatever this side computes
+                    if (!lj) pruned = pruned_dev(cj, wj, pc.shift[img], a.tc, a.tw, a.cutoff, a.theta, a.longshort) | (sons.x < 0) | (sons.y < 0);
                     cj[0] += pc.shift[img][0]; cj[1] += pc.shift[img][1]; cj[2] += pc.shift[img][2];   // src/remotes.c:73-75
                 }
                 int f = accept_dev(wi, wj, ci[0] - cj[0], ci[1] - cj[1], ci[2] - cj[2], a.cutoff, a.theta, a.longshort);
@@ -365,7 +366,7 @@ struct LeafWalk {
                 double cj[3] = {r0.x, r0.y, r1.x}, wj[3] = {r1.y, r2.x, r2.y};
                 int pruned = 0;
                 if (img != 0 || jm >= a.rleaf0) {
-                    pruned = pruned_dev(cj, wj, pc.shift[img], a.tc, a.tw, a.cutoff, a.theta, a.longshort);
+                    pruned = pruned_dev(cj, wj, pc.shift[img], a.tc, a.tw, a.cutoff, a.theta, a.longshort) | (sons.x < 0) | (sons.y < 0);
                     cj[0] += pc.shift[img][0]; cj[1] += pc.shift[img][1]; cj[2] += pc.shift[img][2];
                 }
                 const int f = accept_dev(sink_g + 3, wj, sink_g[0] - cj[0], sink_g[1] - cj[1], sink_g[2] - cj[2], a.cutoff, a.theta,
@@ -598,16 +599,25 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, LEAF_MIN_BLOCKS) walk_fused_k
 
 // Leaf tiles (FP32 mode): slot j of tile t <- particle j of the leaf, packed-pair layout; tile nt = all padding.
 // Tiles 0..nleaf-1 are the local leaves, nleaf.. the received LET leaves (cells rleaf0..).
+// With the long/short split the tile layout carries no weight (pn2_p2p.cuh): a padding slot is harmless because
+// 2^(-r'^2) flushes to 0 at its distance, which holds while every real particle stays within PN2_PAD_SAFE lambda of
+// its leaf centre per dimension (|sink - pad| >= sqrt(3) (24 - 3 B - 2.71) >= 11.3 lambda for B <= 4.9; leaf pairs
+// are listed only when their boxes are closer than the cut-off, 2.71 lambda).  Wider leaves (NSIDE far finer than the
+// particle spacing) are reported instead of being evaluated wrongly: counters[3] |= 4.
+#define PN2_PAD_SAFE 4.9f
 template <int SW>
 __global__ void tile_kernel(int nt, int nleaf, int rleaf0, const LeafDesc *__restrict__ desc, const float4 *__restrict__ rel,
-                            float *__restrict__ tiles) {
+                            float *__restrict__ tiles, int longshort, unsigned long long *__restrict__ counters) {
     const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const int tile = (int)(t / SW), j = (int)(t % SW);
     if (tile > nt) return;
     float4 p = make_float4(PN2_PAD_COORD, PN2_PAD_COORD, PN2_PAD_COORD, 0.f);
     if (tile < nt) {
         const LeafDesc d = desc[tile < nleaf ? tile : tile - nleaf + rleaf0];
-        if (j < d.npart) p = rel[d.first + j];
+        if (j < d.npart) {
+            p = rel[d.first + j];
+            if (longshort && fmaxf(fmaxf(fabsf(p.x), fabsf(p.y)), fabsf(p.z)) > PN2_PAD_SAFE) atomicOr(&counters[3], 4ULL);
+        }
     }
     float *o = tiles + (size_t)tile * (4 * SW) + (j >> 1) * 8 + (j & 1);
     o[0] = p.x; o[2] = p.y; o[4] = p.z; o[6] = p.w;
@@ -676,9 +686,9 @@ int pn2_walk_fused(pn2_ctx *h, int dump) {
         PN2_TRY(h->tiles.ensure(((size_t)nt + 1) * 4 * sw));
         const long nthr = ((long)nt + 1) * sw;
         const unsigned g = (unsigned)((nthr + 255) / 256);
-        if (sw == 8) tile_kernel<8><<<g, 256, 0, h->stream>>>(nt, h->nleaf, h->ncell, h->desc.p, h->rel.p, h->tiles.p);
-        else if (sw == 16) tile_kernel<16><<<g, 256, 0, h->stream>>>(nt, h->nleaf, h->ncell, h->desc.p, h->rel.p, h->tiles.p);
-        else tile_kernel<32><<<g, 256, 0, h->stream>>>(nt, h->nleaf, h->ncell, h->desc.p, h->rel.p, h->tiles.p);
+        if (sw == 8) tile_kernel<8><<<g, 256, 0, h->stream>>>(nt, h->nleaf, h->ncell, h->desc.p, h->rel.p, h->tiles.p, h->prm.longshort, h->counters.p);
+        else if (sw == 16) tile_kernel<16><<<g, 256, 0, h->stream>>>(nt, h->nleaf, h->ncell, h->desc.p, h->rel.p, h->tiles.p, h->prm.longshort, h->counters.p);
+        else tile_kernel<32><<<g, 256, 0, h->stream>>>(nt, h->nleaf, h->ncell, h->desc.p, h->rel.p, h->tiles.p, h->prm.longshort, h->counters.p);
         h->launches++;
         a.tiles = h->tiles.p; a.pad_tile = nt;
     }

@@ -6,7 +6,8 @@ where /root/reference does not exist.
 
 Fixtures
   demo_pos_f32.npy            positions of demo/ic_lcdm.gdt2 (float32 block of the Gadget-2 file, N=32768)
-  demo_ns{32,16}_np{1,2,4}.npz  accelerations in input order + counters of one short-range force evaluation
+  demo_ns32_np{1,2,3,4,8}.npz, demo_ns16_np{1,2,4}.npz
+                              accelerations in input order + counters of one short-range force evaluation
                               (demo/lcdm_g2.run parameters: MaxPackage 8, OPENANGLE 0.4; NSIDE 16 exercises M2L)
   small_{t04,t12}_np{1,2}.npz every 8th demo particle (N=4096), NSIDE 24, theta 0.4 / 1.2: accelerations, full tree
                               arrays (leaves, nodes, M, L after the step) and full local P2P/M2L lists per rank
@@ -44,8 +45,8 @@ def main():
     np.save(os.path.join(HERE, "demo_pos_f32.npy"), pos.astype(np.float32))
     assert np.array_equal(pos.astype(np.float32).astype(np.float64), pos)
     for nside in (32, 16):
-        for nranks in (1, 2, 4):
-            if nside == 16 and nranks == 4:
+        for nranks in (1, 2, 3, 4, 8):
+            if nside == 16 and nranks in (3, 8):
                 continue
             r = pn_ref.run_reference(pos, box, nside, mass, maxleaf=8, theta=0.4, nranks=nranks, capture=1, timeout=600)
             acc = pn_ref.gather_acc(r, len(pos))

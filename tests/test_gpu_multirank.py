@@ -4,7 +4,8 @@ walks against received trees.  Ranks are contexts of one process exchanging devi
 (tests/test_nccl_two_gpus.py, bench.py --gpus N).
 
 Checked against (1) the oracle's multi-rank evaluation on Mode-B trees (reference-pinned walkers / LET pack),
-(2) the UNMODIFIED reference's NP=2 / NP=4 golden accelerations of the demo IC."""
+(2) the UNMODIFIED reference's NP = 2, 3, 4 and 8 golden accelerations of the demo IC (src/remotes.c:684-751,
+src/fmm.c:1021-1045 at the rank counts BASELINE.md's runs used)."""
 import numpy as np
 import pytest
 
@@ -58,9 +59,9 @@ def test_small_vs_oracle(pn2, oracle, small_pos, tag, nranks):
             assert sum(i["n_m2l_pairs"] for i in infos) > 1000
 
 
-@pytest.mark.parametrize("nside,nranks", [(32, 2), (32, 4), (16, 2)])
+@pytest.mark.parametrize("nside,nranks", [(32, 2), (32, 3), (32, 4), (32, 8), (16, 2), (16, 4)])
 def test_demo_vs_reference_golden(pn2, oracle, demo_pos, nside, nranks):
-    """The reference itself at NP=2 / NP=4 (tests/golden/demo_ns*_np*.npz): same domain rule, same trees' leaf sets,
+    """The reference itself at NP = 2, 3, 4, 8 (tests/golden/demo_ns*_np*.npz): same domain rule, same trees' leaf sets,
     same lists -> FP64 mode agrees to rounding, FP32 mode within 1e-4."""
     g = load_golden(f"demo_ns{nside}_np{nranks}.npz")
     prm_o = oracle.make_params(float(g["box"]), nside, len(demo_pos), float(g["mass"]), maxleaf=8, theta=0.4)

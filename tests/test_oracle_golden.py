@@ -16,8 +16,8 @@ def _hash(s, t):
     return h.hexdigest()
 
 
-@pytest.mark.parametrize("name,nranks", [("demo_ns32_np1", 1), ("demo_ns32_np2", 2), ("demo_ns32_np4", 4),
-                                         ("demo_ns16_np1", 1), ("demo_ns16_np2", 2)])
+@pytest.mark.parametrize("name,nranks", [("demo_ns32_np1", 1), ("demo_ns32_np2", 2), ("demo_ns32_np3", 3), ("demo_ns32_np4", 4),
+                                         ("demo_ns32_np8", 8), ("demo_ns16_np1", 1), ("demo_ns16_np2", 2), ("demo_ns16_np4", 4)])
 def test_force_matches_reference(oracle, demo_pos, name, nranks):
     g = load_golden(name + ".npz")
     prm = oracle.make_params(float(g["box"]), int(g["nside"]), len(demo_pos), float(g["mass"]), maxleaf=int(g["maxleaf"]),
