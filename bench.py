@@ -312,7 +312,7 @@ def main():
     for _ in range(args.warmup):
         step()
     barrier()
-    fma_peak = ctx.fma_peak(False)
+    fma_peak = ctx.fma_peak(precision != pn2gpu.FP32)     # FFMA issue rate (FP32 mode) / DFMA issue rate (FP64 mode)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -380,7 +380,8 @@ def main():
         return
     pps = n_total / (ms_step * 1e-3)
     ach = OPS_PER_INTERACTION * (nint_total / world) / (walk_ms * 1e-3)     # per GPU, dominant kernel
-    nominal = 148 * 128 * (clocks["sm_mhz"] or 1965.0) * 1e6 if clocks else None
+    fp32 = precision == pn2gpu.FP32
+    nominal = 148 * (128 if fp32 else 64) * (clocks["sm_mhz"] or 1965.0) * 1e6 if clocks else None
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -392,7 +393,8 @@ def main():
         try:
             tj = json.load(open(tp))
             # ncu capture of a smaller launch: scale the measured DRAM bytes by the launch's interaction count
-            traffic = tj["walk_fused_dram_bytes_per_launch"] / tj["interactions_per_launch"] * (nint_total / world)
+            key = "walk_fused" if fp32 else "walk_fused_f64"
+            traffic = tj[key + "_dram_bytes_per_launch"] / tj.get(key + "_interactions_per_launch", tj.get("interactions_per_launch")) * (nint_total / world)
         except Exception:
             traffic = None
     out = {"metric": METRIC, "value": pps, "unit": "particles/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -406,11 +408,13 @@ def main():
            "tree": {"nleaf": info["nleaf"], "nnode": info["nnode"], "levels": info["nlevel"], "m2l_pairs": info["n_m2l_pairs"],
                     "p2p_leaf_pairs": info["n_p2p_pairs"], "walk_visits": info["n_walk_visits"],
                     "frontier_bytes": info["frontier_bytes"]},
-           "roofline": {"bound": "fma_pipe", "kernel": "walk_fused_kernel (list walk + P2P)", "achieved": ach / 1e12,
-                        "peak": fma_peak / 1e12, "unit": "Tops/s (FFMA/FMUL/FADD issue slots)", "frac": ach / fma_peak,
-                        "peak_source": "measured in this run: pn2_fma_peak (independent FFMA chains, CUDA events)",
+           "roofline": {"bound": "fma_pipe", "kernel": ("walk_fused_kernel" if fp32 else "walk_fused_f64_kernel") + " (list walk + P2P)",
+                        "achieved": ach / 1e12, "peak": fma_peak / 1e12,
+                        "unit": "Tops/s (FFMA/FMUL/FADD issue slots)" if fp32 else "Tops/s (DFMA/DMUL/DADD issue slots)", "frac": ach / fma_peak,
+                        "peak_source": "measured in this run: pn2_fma_peak (independent %s chains, CUDA events)" % ("FFMA" if fp32 else "DFMA"),
                         "nominal_peak_at_sampled_clock": (nominal / 1e12) if nominal else None,
-                        "ops_per_interaction": OPS_PER_INTERACTION, "ops_executed_per_interaction": 23, "traffic": traffic,
+                        "ops_per_interaction": OPS_PER_INTERACTION, "ops_executed_per_interaction": 23 if fp32 else 28,
+                        "frac_executed": (23 if fp32 else 28) / OPS_PER_INTERACTION * ach / fma_peak, "traffic": traffic,
                         "hbm_peak_gbs_measured": peaks.get("hbm_gbs")},
            "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e}
     if not args.no_cpu_baseline and world == 1:

@@ -42,8 +42,11 @@ typedef enum {
 } pn2_status;
 
 /* arithmetic modes of the P2P kernel (the multipole operators always run in FP64) */
-#define PN2_FP64 0              /* double differences, libm-grade erfc/exp: parity mode, rms <= 1e-6 */
+#define PN2_FP64 0              /* double arithmetic throughout; Mode B: g(u) from a piecewise degree-8 table (|err| < 7e-11),
+                                   rsqrt seed + Newton step, no libm: rms <= 1e-6 (measured ~1e-11) */
 #define PN2_FP32 1              /* leaf-centre-relative float4 sources, rsqrt + ex2 + polynomial g(u): rms <= 1e-4 */
+#define PN2_FP64_LIBM 2         /* the reference's own expression (sqrt, division, erfc, exp: src/fmm.c:834-852); slow,
+                                   kept as the checker of the PN2_FP64 table kernel */
 
 /* run parameters: globals of inc/photoNs.h:20-44,124-126, derived in src/initial.c:316-345 */
 typedef struct {
@@ -56,7 +59,7 @@ typedef struct {
     int32_t maxleaf;            /* MAXLEAF (MaxPackage), 1..32 */
     int32_t periodic;           /* built with -DPERIODIC_CONDITION */
     int32_t longshort;          /* built with -DLONGSHORT */
-    int32_t precision;          /* PN2_FP64 | PN2_FP32 */
+    int32_t precision;          /* PN2_FP64 | PN2_FP32 | PN2_FP64_LIBM */
 } pn2_params;
 
 /* byte-compatible views of the reference structs (sizes probed: 376, 392, 224, 32, 96 bytes) */

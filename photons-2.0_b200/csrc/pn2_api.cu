@@ -42,7 +42,7 @@ static int check_params(const pn2_params *p) {
     if (!p) { pn2_set_error("pn2: params is NULL"); return PN2_ERR_ARG; }
     if (p->maxleaf < 1 || p->maxleaf > 32) { pn2_set_error("pn2: maxleaf %d outside 1..32", p->maxleaf); return PN2_ERR_ARG; }
     if (!(p->rs > 0.0) || !(p->box > 0.0)) { pn2_set_error("pn2: rs and box must be positive"); return PN2_ERR_ARG; }
-    if (p->precision != PN2_FP64 && p->precision != PN2_FP32) { pn2_set_error("pn2: unknown precision %d", p->precision); return PN2_ERR_ARG; }
+    if (p->precision != PN2_FP64 && p->precision != PN2_FP32 && p->precision != PN2_FP64_LIBM) { pn2_set_error("pn2: unknown precision %d", p->precision); return PN2_ERR_ARG; }
     return PN2_OK;
 }
 
@@ -88,7 +88,7 @@ extern "C" int pn2_destroy(pn2_ctx *h) {
     if (!h) return PN2_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    h->pos.release(); h->acc.release(); h->rel.release(); h->tiles.release(); h->rec_pos.release(); h->rec_acc.release(); h->geom.release(); h->son.release(); h->desc.release();
+    h->pos.release(); h->acc.release(); h->rel.release(); h->tiles.release(); h->tiles64.release(); h->gtab.release(); h->rec_pos.release(); h->rec_acc.release(); h->geom.release(); h->son.release(); h->desc.release();
     h->M.release(); h->L.release(); h->level_nodes.release(); h->r_desc.release(); h->r_geom.release();
     h->r_M.release(); h->r_pos.release(); h->r_rel.release(); h->ia.release(); h->ib.release(); h->ic.release();
     h->id_.release(); h->la.release(); h->ua.release(); h->ub.release(); h->tmp.release(); h->counters.release();

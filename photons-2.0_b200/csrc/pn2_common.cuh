@@ -98,6 +98,8 @@ struct pn2_ctx {
     DBuf<double> acc;          // [n][3]
     DBuf<float4> rel;          // [n]
     DBuf<float> tiles;         // Mode B FP32: leaf tiles, [nleaf + received leaves + 1][SW * 4]
+    DBuf<double> tiles64;      // Mode B FP64: leaf tiles, [nleaf + received leaves + 1][SW][4]
+    DBuf<double> gtab;         // FP64 mode: g(u) table (pn2_gtab.h)
     // ---- cells: leaves 0..nleaf-1, nodes nleaf..nleaf+nnode-1 ----
     int nleaf = 0, nnode = 0, ncell = 0, nlevel = 0;
     int first_leaf = 0, last_leaf = 0, first_node = 0, last_node = 0;   // Mode A id space

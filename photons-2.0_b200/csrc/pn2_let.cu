@@ -223,7 +223,7 @@ int pn2_let_pack_all(pn2_ctx *h) {
     LetState *L = let_state(h);
     cudaStream_t st = h->stream;
     const int np = L->npeer, nleaf = h->nleaf, nnode = h->nnode, ncell = h->ncell;
-    L->psize = h->prm.precision == PN2_FP64 ? 24 : 16;
+    L->psize = h->prm.precision != PN2_FP32 ? 24 : 16;
     L->s_nl.assign(np, 0); L->s_nn.assign(np, 0); L->s_np.assign(np, 0);
     if (np == 0) return PN2_OK;
     std::vector<double> tb(6 * (size_t)np);
@@ -280,7 +280,7 @@ int pn2_let_pack_all(pn2_ctx *h) {
                                                                    h->son.p, h->desc.p, h->M.p, L->send_leaf.p + ol, L->send_node.p + on);
         long ntp = (long)nleaf * h->prm.maxleaf;
         let_pack_parts_kernel<<<(unsigned)((ntp + 255) / 256), 256, 0, st>>>(p, nleaf, ncell, h->prm.maxleaf, L->reach.p, L->pidx.p, h->desc.p,
-                                                                            h->rel.p, h->pos.p, h->prm.precision == PN2_FP64,
+                                                                            h->rel.p, h->pos.p, h->prm.precision != PN2_FP32,
                                                                             L->send_part.p + (size_t)op * L->psize);
         h->launches += 2;
         ol += L->s_nl[p]; on += L->s_nn[p]; op += L->s_np[p];
@@ -394,7 +394,7 @@ int pn2_let_unpack(pn2_ctx *h) {
         size_t nc = (size_t)h->ncell + rl + rn;
         PN2_TRY(h->geom.ensure(6 * nc + 6, true, st)); PN2_TRY(h->son.ensure(2 * nc + 2, true, st)); PN2_TRY(h->desc.ensure(nc + 1, true, st));
         PN2_TRY(h->M.ensure(NM * nc + NM, true, st));
-        if (h->prm.precision == PN2_FP64) PN2_TRY(h->pos.ensure(3 * ((size_t)h->n + rp) + 3, true, st));
+        if (h->prm.precision != PN2_FP32) PN2_TRY(h->pos.ensure(3 * ((size_t)h->n + rp) + 3, true, st));
         else PN2_TRY(h->rel.ensure((size_t)h->n + rp + 1, true, st));
         long ol = 0, on = 0, op = 0;
         for (int p = 0; p < np; p++) {
@@ -410,7 +410,7 @@ int pn2_let_unpack(pn2_ctx *h) {
             ol += nl; on += nn; op += L->r_np[p];
         }
         if (rp > 0) {
-            if (h->prm.precision == PN2_FP64)
+            if (h->prm.precision != PN2_FP32)
                 CUDA_TRY(cudaMemcpyAsync(h->pos.p + 3 * (size_t)h->n, L->recv_part.p, (size_t)rp * 24, cudaMemcpyDeviceToDevice, st));
             else
                 CUDA_TRY(cudaMemcpyAsync(h->rel.p + h->n, L->recv_part.p, (size_t)rp * 16, cudaMemcpyDeviceToDevice, st));

@@ -180,7 +180,7 @@ int pn2_launch_relpos(pn2_ctx *h, const double *pos, const LeafDesc *desc, int n
 template <int SW>
 static int launch_sw(pn2_ctx *h, const CsrList &list, const SourceSet &src, int local) {
     unsigned grid = (unsigned)((list.nseg + P2P_WARPS - 1) / P2P_WARPS);
-    if (h->prm.precision == PN2_FP64) {
+    if (h->prm.precision != PN2_FP32) {
         p2p_csr_f64_kernel<SW><<<grid, P2P_WARPS * 32, 0, h->stream>>>(list.nseg, list.seg_sink, list.seg_off, list.src,
                                                                        h->desc.p, h->pos.p, src.desc, src.pos, h->acc.p,
                                                                        h->pc, h->counters.p, local);

@@ -41,6 +41,8 @@ struct WalkArgs {
     const LeafDesc *desc;
     const int *parent;
     const float *tiles;                // FP32 mode: leaf tiles (see walk_fused_kernel), pad_tile = the all-padding tile
+    const double *tiles64;             // FP64 mode: leaf tiles of {x, y, z, w} doubles (walk_fused_f64_kernel)
+    const double *gtab;                // FP64 mode: piecewise-polynomial table of g(u) (pn2_gtab.h)
     int pad_tile;
     const double *pos;
     double *acc;
@@ -290,7 +292,8 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NODE_MIN_BLOCKS) frontier_nod
 // finds to a per-warp queue of 16-byte entries:
 //     FP32 mode (MODE 0): {tile, dx, dy, dz}  tile = leaf tile index, d = source leaf centre - sink leaf centre
 //                                             (+ image shift) in units of lambda = 2 rs sqrt(ln 2)
-//     FP64 / dump modes : {first, npart, cell | image << 26, 0}
+//     FP64 libm / dump modes (1, 2): {first, npart, cell | image << 26, 0}
+//     FP64 tile mode (MODE 3): two int4 per entry: {tile, 0, dx (double)}, {dy, dz (doubles)}, d in units of 2 rs
 template <int MODE, int QCAP>      // QCAP = queue capacity: a power of two > (entries a consumer leaves queued, < 32) + 32
 struct LeafWalk {
     SpanReader rd;
@@ -345,7 +348,7 @@ struct LeafWalk {
         // ---- phase 2: decide, then compact pushes / queue entries / M2L pairs with ballots ----
         int npush = 0, emit_p = 0, emit_m = 0;
         unsigned p0 = 0, p1 = 0;
-        int4 ent = make_int4(0, 0, 0, 0);
+        int4 ent = make_int4(0, 0, 0, 0), ent2 = ent;
         if (lane < k) {
             const int jm = (int)(jme & PN2_CELL_MASK);
             const unsigned img = jme >> PN2_IMG_SHIFT, imgbits = jme & ~PN2_CELL_MASK;
@@ -358,6 +361,12 @@ struct LeafWalk {
                     ent.y = __float_as_int((float)(((r0.x + pc.shift[img][0]) - sd.c[0]) * pc.inv_len));
                     ent.z = __float_as_int((float)(((r0.y + pc.shift[img][1]) - sd.c[1]) * pc.inv_len));
                     ent.w = __float_as_int((float)(((r1.x + pc.shift[img][2]) - sd.c[2]) * pc.inv_len));
+                } else if (MODE == 3) {
+                    const double ox = ((r0.x + pc.shift[img][0]) - sd.c[0]) * pc.inv2rs;
+                    const double oy = ((r0.y + pc.shift[img][1]) - sd.c[1]) * pc.inv2rs;
+                    const double oz = ((r1.x + pc.shift[img][2]) - sd.c[2]) * pc.inv2rs;
+                    ent = make_int4(jm < a.nleaf ? jm : jm - a.rleaf0 + a.nleaf, 0, __double2loint(ox), __double2hiint(ox));
+                    ent2 = make_int4(__double2loint(oy), __double2hiint(oy), __double2loint(oz), __double2hiint(oz));
                 } else {
                     ent = make_int4(dfirst, dnpart, (int)jme, 0);
                 }
@@ -384,7 +393,12 @@ struct LeafWalk {
         if (top > STACK_CAP) { err = 1; return false; }
         if (npush == 2) { stack[pos0] = p0; stack[pos0 + 1] = p1; }
         const unsigned mp = __ballot_sync(0xffffffffu, emit_p);
-        if (emit_p) queue[(qtail + __popc(mp & lt_mask)) & (QCAP - 1)] = ent;
+        if (MODE == 3) {
+            if (emit_p) {
+                const int at = 2 * ((qtail + __popc(mp & lt_mask)) & (QCAP - 1));
+                queue[at] = ent; queue[at + 1] = ent2;
+            }
+        } else if (emit_p) queue[(qtail + __popc(mp & lt_mask)) & (QCAP - 1)] = ent;
         qtail += __popc(mp);
         npairs += __popc(mp);
         emit_m2l_pairs(a, lane, lt_mask, emit_m, (unsigned)leaf, jme);
@@ -597,6 +611,200 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, LEAF_MIN_BLOCKS) walk_fused_k
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// FP64 product kernel: the same fused walk + P2P with double tiles and no libm
+// ------------------------------------------------------------------------------------------------
+// Tiles: SW slots of {x, y, z, w} doubles (32 bytes), leaf-centre-relative in units of 2 rs (so u = r), w = 1, padding
+// slots far away with w = 0.  Arithmetic per interaction (reference: src/fmm.c:834-852, sqrt + division + erfc + exp
+// from libm): 3 DADD + 3 DFMA (r^2) + MUFU.RSQ64H and one Newton step (4 ops, relative error < 1e-12) + 1 DSETP
+// (softening) + 2 DMUL (1/r^3) + DMUL (u) + 2 ops and F2I / I2F (interval of the g(u) table) + 8 DFMA (degree-8
+// piece of g, |error| < 7e-11: pn2_gtab.h, tools/fit_g64.py) + DMUL + 3 DFMA = 28 FP64-pipe operations.
+#include "pn2_gtab.h"
+#ifndef F64_MIN_BLOCKS
+#define F64_MIN_BLOCKS 4
+#endif
+#define F64_NST 4
+template <int SW>
+struct Fused64Layout {
+    static constexpr int NSL = 32 / SW;
+    static constexpr int NST = F64_NST;
+    static constexpr int BATCH = NST * NSL;               // source leaves per batch (16 / 8 / 4)
+    static constexpr int TB = 32 * SW;                    // tile bytes
+    static constexpr int ROWB = TB + 32;                  // + {dx, dy, dz, -} of the leaf
+    static constexpr int STAGE_BYTES = BATCH * ROWB;
+};
+__device__ __forceinline__ double pn2_rsqrt64(double x) {   // MUFU.RSQ64H: ~20-bit seed
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+}
+struct P2PSink64 {
+    double nx, ny, nz;        // centre offset - x_i
+    double ax[2], ay[2], az[2];
+};
+template <bool LS>
+__device__ __forceinline__ void p2p_interact_tab64(const double *slot, P2PSink64 &sk, int par, double eps2, double inv_eps,
+                                                   const double (*gtab)[PN2_GTAB_K]) {
+    const double2 xy = *reinterpret_cast<const double2 *>(slot);
+    double zz, ww = 1.0;
+    if (LS) zz = slot[2];
+    else { const double2 zw = *reinterpret_cast<const double2 *>(slot + 2); zz = zw.x; ww = zw.y; }
+    const double dx = xy.x + sk.nx, dy = xy.y + sk.ny, dz = zz + sk.nz;
+    double r2 = fma(dx, dx, 1e-200);
+    r2 = fma(dy, dy, r2);
+    r2 = fma(dz, dz, r2);
+    const double y0 = pn2_rsqrt64(r2);
+    const double hh = r2 * y0;
+    const double e = fma(-hh, y0, 1.0);
+    const double rinv = fma(0.5 * y0, e, y0);                 // one Newton step
+    const double ir = r2 < eps2 ? inv_eps : rinv;             // src/fmm.c:839-843
+    double s = ir * ir * ir;
+    if (LS) {
+        const double u = r2 * rinv;
+        const double t = fma(u, PN2_GTAB_INVH, -0.5);
+        const int k = __double2int_rn(t);                     // interval of u (round-to-nearest of u / h - 1/2)
+        const double d = t - (double)k;
+        const int kc = k < PN2_GTAB_K - 1 ? k : PN2_GTAB_K - 1;   // u >= 6: the zero entry
+        double g = gtab[PN2_GTAB_DEG][kc];
+#pragma unroll
+        for (int j = PN2_GTAB_DEG - 1; j >= 0; j--) g = fma(g, d, gtab[j][kc]);
+        s *= g;
+    } else {
+        s *= ww;
+    }
+    sk.ax[par] = fma(dx, s, sk.ax[par]);
+    sk.ay[par] = fma(dy, s, sk.ay[par]);
+    sk.az[par] = fma(dz, s, sk.az[par]);
+}
+
+template <int SW, bool LS>
+__global__ void __launch_bounds__(WALK_WARPS * 32, F64_MIN_BLOCKS) walk_fused_f64_kernel(WalkArgs a, P2PConst pc) {
+    using FL = Fused64Layout<SW>;
+    constexpr int NSL = FL::NSL, NST = FL::NST, BATCH = FL::BATCH, TB = FL::TB, ROWB = FL::ROWB;
+    __shared__ unsigned s_stack[WALK_WARPS][STACK_CAP];
+    __shared__ int4 s_srcq[WALK_WARPS][2 * SRCQ_CAP];
+    __shared__ __align__(16) unsigned char s_stage[WALK_WARPS][FL::STAGE_BYTES];
+    __shared__ double s_sink[WALK_WARPS][6];
+    __shared__ __align__(128) double s_gtab[PN2_GTAB_DEG + 1][PN2_GTAB_K];
+    for (int i = threadIdx.x; i < (PN2_GTAB_DEG + 1) * PN2_GTAB_K; i += blockDim.x) (&s_gtab[0][0])[i] = a.gtab[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int leaf = blockIdx.x * WALK_WARPS + wib;
+    if (leaf >= a.nleaf) return;
+    const int q = lane / SW, j = lane % SW;
+    LeafWalk<3, SRCQ_CAP> w;
+    w.begin(a, leaf, s_stack[wib], s_srcq[wib], s_sink[wib], lane);
+    double xi, yi, zi;
+    {
+        const double *t = a.tiles64 + ((size_t)leaf * SW + j) * 4;
+        xi = t[0]; yi = t[1]; zi = t[2];
+    }
+    P2PSink64 sk;
+    sk.nx = sk.ny = sk.nz = 0.0;
+    sk.ax[0] = sk.ax[1] = sk.ay[0] = sk.ay[1] = sk.az[0] = sk.az[1] = 0.0;
+    const double eps = pc.soft * pc.inv2rs;
+    const double eps2 = eps * eps, inv_eps = eps > 0.0 ? 1.0 / eps : 1e100;
+
+    int qhead = 0, inflight = 0;
+    unsigned char *stage = s_stage[wib];
+    const unsigned stage_dst = (unsigned)__cvta_generic_to_shared(stage) + q * ROWB + j * 16;   // first of this lane's two chunks
+    const char *tile_src = reinterpret_cast<const char *>(a.tiles64) + j * 16;
+    auto issue_batch = [&](int cnt) {      // cnt <= BATCH queue entries from qhead, a multiple of NSL
+#pragma unroll
+        for (int s = 0; s < NST; s++) {
+            if (s * NSL < cnt) {
+                const int qi = 2 * ((qhead + s * NSL + q) & (SRCQ_CAP - 1));
+                const int4 e0 = w.queue[qi];
+                const char *src = tile_src + (size_t)e0.x * TB;
+                cp_async16(stage_dst + s * NSL * ROWB, src);
+                cp_async16(stage_dst + s * NSL * ROWB + SW * 16, src + SW * 16);
+                if (j == 0) {
+                    int4 *hd = reinterpret_cast<int4 *>(stage + (s * NSL + q) * ROWB + TB);
+                    hd[0] = e0; hd[1] = w.queue[qi + 1];
+                }
+            }
+        }
+        cp_async_commit();
+        inflight = cnt;
+        qhead += cnt;
+    };
+    auto compute_stage = [&](int s) {
+        const double *row = reinterpret_cast<const double *>(stage + (s * NSL + q) * ROWB);
+        const double *hd = row + TB / 8;
+        sk.nx = hd[1] - xi; sk.ny = hd[2] - yi; sk.nz = hd[3] - zi;
+#pragma unroll
+        for (int k = 0; k < SW; k++) p2p_interact_tab64<LS>(row + 4 * k, sk, k & 1, eps2, inv_eps, s_gtab);
+    };
+    auto compute_batch = [&]() {
+        cp_async_wait_all();
+        __syncwarp();
+#pragma unroll 1
+        for (int s = 0; s * NSL < inflight; s++) compute_stage(s);
+        inflight = 0;
+        __syncwarp();
+    };
+    bool walking = true;
+    while (true) {
+        while (walking && w.qtail - qhead < BATCH) walking = w.step(a, pc, lane);
+        if (inflight) compute_batch();
+        const int avail = w.qtail - qhead;
+        if (avail == 0 || w.err) break;
+        int cnt = BATCH;
+        if (avail < BATCH) {
+            cnt = ((avail + NSL - 1) / NSL) * NSL;
+            if (lane < cnt - avail) {
+                const int at = 2 * ((w.qtail + lane) & (SRCQ_CAP - 1));
+                w.queue[at] = make_int4(a.pad_tile, 0, 0, 0); w.queue[at + 1] = make_int4(0, 0, 0, 0);
+            }
+            w.qtail = qhead + cnt;
+            __syncwarp();
+        }
+        issue_batch(cnt);
+    }
+    if (w.err) { if (lane == 0) atomicOr(&a.counters[3], 1ULL); return; }
+
+    double ax = sk.ax[0] + sk.ax[1], ay = sk.ay[0] + sk.ay[1], az = sk.az[0] + sk.az[1];
+#pragma unroll
+    for (int m = SW; m < 32; m <<= 1) {
+        ax += __shfl_xor_sync(0xffffffffu, ax, m);
+        ay += __shfl_xor_sync(0xffffffffu, ay, m);
+        az += __shfl_xor_sync(0xffffffffu, az, m);
+    }
+    const LeafDesc sd = w.sd;
+    if (q == 0 && j < sd.npart) {
+        const double sc = pc.mass * pc.inv2rs * pc.inv2rs;
+        double *o = a.acc + 3 * (size_t)(sd.first + j);
+        o[0] += ax * sc; o[1] += ay * sc; o[2] += az * sc;
+    }
+    unsigned nsrc = w.nsrc;
+#pragma unroll
+    for (int m = 1; m < 32; m <<= 1) nsrc += __shfl_xor_sync(0xffffffffu, nsrc, m);
+    if (lane == 0) {
+        atomicAdd(&a.counters[0], (unsigned long long)nsrc * (unsigned long long)sd.npart);
+        atomicAdd(&a.counters[2], (unsigned long long)w.npairs);
+        atomicAdd(&a.counters[4], (unsigned long long)w.visits);
+    }
+}
+
+// FP64 tiles: slot j of tile t <- (pos - leaf centre) / (2 rs) of particle j, w = 1; padding far away with w = 0
+template <int SW>
+__global__ void tile64_kernel(int nt, int nleaf, int rleaf0, const LeafDesc *__restrict__ desc, const double *__restrict__ pos,
+                              double inv2rs, double *__restrict__ tiles) {
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int tile = (int)(t / SW), j = (int)(t % SW);
+    if (tile > nt) return;
+    double4 p = make_double4(1e4, 1e4, 1e4, 0.0);
+    if (tile < nt) {
+        const LeafDesc d = desc[tile < nleaf ? tile : tile - nleaf + rleaf0];
+        if (j < d.npart) {
+            const double *x = pos + 3 * (size_t)(d.first + j);
+            p = make_double4((x[0] - d.c[0]) * inv2rs, (x[1] - d.c[1]) * inv2rs, (x[2] - d.c[2]) * inv2rs, 1.0);
+        }
+    }
+    double2 *o = reinterpret_cast<double2 *>(tiles + ((size_t)tile * SW + j) * 4);
+    o[0] = make_double2(p.x, p.y); o[1] = make_double2(p.z, p.w);
+}
+
 // Leaf tiles (FP32 mode): slot j of tile t <- particle j of the leaf, packed-pair layout; tile nt = all padding.
 // Tiles 0..nleaf-1 are the local leaves, nleaf.. the received LET leaves (cells rleaf0..).
 // With the long/short split the tile layout carries no weight (pn2_p2p.cuh): a padding slot is harmless because
@@ -628,6 +836,8 @@ static void launch_mode(pn2_ctx *h, const WalkArgs &a, int mode) {
     const unsigned grid = (unsigned)((a.nleaf + WALK_WARPS - 1) / WALK_WARPS);
     if (mode == 0 && h->prm.longshort) walk_fused_kernel<SW, true><<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
     else if (mode == 0) walk_fused_kernel<SW, false><<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
+    else if (mode == 3 && h->prm.longshort) walk_fused_f64_kernel<SW, true><<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
+    else if (mode == 3) walk_fused_f64_kernel<SW, false><<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
     else if (mode == 1) walk_leaf_kernel<SW, 1><<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
     else walk_leaf_kernel<SW, 2><<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
     h->launches++;
@@ -677,8 +887,25 @@ int pn2_walk_fused(pn2_ctx *h, int dump) {
     fill_args(h, a);
     a.pass = dump == 2 ? 1 : 0;
     a.emit_m2l = dump == 0;
-    int mode = dump ? 2 : (h->prm.precision == PN2_FP64 ? 1 : 0);
+    // PN2_FP64: table-driven FP64 kernel (3); PN2_FP64_LIBM: the reference's expression with libm (1); PN2_FP32: 0
+    int mode = dump ? 2 : (h->prm.precision == PN2_FP64 ? 3 : (h->prm.precision == PN2_FP64_LIBM ? 1 : 0));
     int ml = h->prm.maxleaf;
+    if (mode == 3) {
+        const int sw = ml <= 8 ? 8 : (ml <= 16 ? 16 : 32);
+        const int nt = h->nleaf + h->nrl;
+        PN2_TRY(h->tiles64.ensure(((size_t)nt + 1) * 4 * sw));
+        if (!h->gtab.p) {
+            PN2_TRY(h->gtab.ensure((PN2_GTAB_DEG + 1) * PN2_GTAB_K));
+            CUDA_TRY(cudaMemcpyAsync(h->gtab.p, PN2_GTAB, sizeof PN2_GTAB, cudaMemcpyHostToDevice, h->stream));
+        }
+        const long nthr = ((long)nt + 1) * sw;
+        const unsigned g = (unsigned)((nthr + 255) / 256);
+        if (sw == 8) tile64_kernel<8><<<g, 256, 0, h->stream>>>(nt, h->nleaf, h->ncell, h->desc.p, h->pos.p, h->pc.inv2rs, h->tiles64.p);
+        else if (sw == 16) tile64_kernel<16><<<g, 256, 0, h->stream>>>(nt, h->nleaf, h->ncell, h->desc.p, h->pos.p, h->pc.inv2rs, h->tiles64.p);
+        else tile64_kernel<32><<<g, 256, 0, h->stream>>>(nt, h->nleaf, h->ncell, h->desc.p, h->pos.p, h->pc.inv2rs, h->tiles64.p);
+        h->launches++;
+        a.tiles64 = h->tiles64.p; a.gtab = h->gtab.p; a.pad_tile = nt;
+    }
     if (mode == 0) {
         // leaf tiles of the local and the received leaves (+ one padding tile)
         const int sw = ml <= 8 ? 8 : (ml <= 16 ? 16 : 32);

@@ -13,7 +13,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libpn2gpu.so")
 NM = 20
-FP64, FP32 = 0, 1
+FP64, FP32, FP64_LIBM = 0, 1, 2       # include/pn2gpu.h: PN2_FP64 (table-driven, no libm), PN2_FP32, PN2_FP64_LIBM (checker)
 
 # struct layouts of the reference (inc/typesdef.h:25-57, inc/photoNs.h:177-189); sizes 96/376/392/224/32
 BODY = np.dtype([("pos", "f8", 3), ("acc", "f8", 3), ("vel", "f8", 3), ("acc_pm", "f8", 3)])

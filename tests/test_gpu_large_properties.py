@@ -45,6 +45,12 @@ def test_fp32_vs_fp64_and_invariants(pn2, workload):
     err = np.sqrt(((a32 - a64) ** 2).sum() / (a64 ** 2).sum())
     print(f"{SIDE}^3: FP32 mode vs FP64 mode rms rel err {err:.3e}; {i64['n_interactions'] / n:.1f} interactions/particle")
     assert err <= 1e-4
+    # the table-driven FP64 kernel (no libm) against the reference's own expression evaluated with libm erfc / exp / sqrt
+    clm, alm = run(pn2, pos, box, mass, pn2.FP64_LIBM)
+    err = np.sqrt(((a64 - alm) ** 2).sum() / (alm ** 2).sum())
+    print(f"{SIDE}^3: FP64 table kernel vs libm expression (src/fmm.c:834-852) rms rel err {err:.3e}")
+    assert err <= 2e-9 and clm.step_info()["n_interactions"] == i64["n_interactions"]
+    clm.close()
 
     # momentum balance (uniform mass): |sum a| against sum |a|
     for a, tol in ((a64, 1e-6), (a32, 1e-5)):
