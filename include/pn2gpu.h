@@ -214,6 +214,28 @@ int pn2_drift_device(pn2_ctx *h, double *d_body, int n, double dd, double box);
  * Same result as pn2_force_step_device on the packed positions. */
 int pn2_force_step_records(pn2_ctx *h, double *d_rec, int rec_doubles, int acc_offset, int n, const pn2_domain *dom);
 
+/* ---- particle-mesh long-range force on the device (src/partmesh.c:18-796, src/conv.f90:128-247) ------
+ * partmesh_thread: CIC deposit of the particles on the NSIDE^3 mesh (:98-178), the mesh all-to-all into the FFT pencils
+ * (:188-352) and back (:430-470), convolution (conv.f90: FFT, Green function pref exp(-k^2 rs^2) sinc^-4 / k^2, inverse
+ * FFT), 4-point gradient of the potential at the 8 CIC cells and CIC gather into Body.acc_pm (:472-775).
+ * Here every rank holds the whole mesh in HBM: the exchange is one ncclAllReduce of the density, the transform is cuFFT
+ * (a library FFT, as 2DECOMP&FFT is for the reference), every rank gathers the force of its own particles.  BOX, rs
+ * (splitRadius) and MASSPART come from pn2_params; nside is the PM mesh side NSIDE.
+ *   pn2_pm_force_device : packed device positions double[n][3] -> acc_pm double[n][3] (overwritten), caller order
+ *   pn2_pm_force_records: on device records (Body: rec_doubles 12, acc_pm_offset 9)
+ *   pn2_pm_begin / pn2_pm_reduce_nccl | pn2_pm_reduce_local / pn2_pm_finish: the phases, for drivers that own the
+ *       reduction (pn2_pm_reduce_local: all ranks are contexts of one process)
+ *   pn2_pm_get_mesh     : inspection (tests): the mesh as it is -- density after begin / reduce, potential after finish
+ *   pn2_pm_get_timings  : ms of the last evaluation: deposit, mesh reduction, FFTs + Green function, gather */
+int pn2_pm_force_device(pn2_ctx *h, const double *d_pos, int n, int nside, double *d_acc_pm);
+int pn2_pm_force_records(pn2_ctx *h, double *d_rec, int rec_doubles, int acc_pm_offset, int n, int nside);
+int pn2_pm_begin(pn2_ctx *h, const double *d_pos, int n, int nside);
+int pn2_pm_reduce_nccl(pn2_ctx *h);
+int pn2_pm_reduce_local(pn2_ctx **hs, int nranks);
+int pn2_pm_finish(pn2_ctx *h, double *d_acc_pm);
+int pn2_pm_get_mesh(pn2_ctx *h, double *mesh_host);
+int pn2_pm_get_timings(pn2_ctx *h, double ms[4]);
+
 /* ---- Mode B inspection (tests: bit-exact tree / list checks; not needed by the product path) --- */
 typedef struct {
     int32_t n, nleaf, nnode, nlevel;

@@ -14,6 +14,7 @@ REF_DIR = os.path.join(HERE, "_ref")
 REF_EXE = os.path.join(REF_DIR, "ref_fmm")
 REF_LIB = os.path.join(REF_DIR, "libphotons_ref.so")
 REF_EXE_OPEN = os.path.join(REF_DIR, "ref_fmm_open")   # built without -DPERIODIC_CONDITION -DLONGSHORT
+REF_EXE_PM = os.path.join(REF_DIR, "ref_pm")          # src/partmesh.c unmodified + C restatement of conv.f90's convolution
 REF_EXE_GPU = os.path.join(REF_DIR, "ref_fmm_gpu")   # the same reference with its task batches routed to libpn2gpu.so
 
 NMULTI = 20
@@ -135,3 +136,28 @@ def gather_acc(ranks, n):
         ids = d["part"]["vel"][:, 0].astype(np.int64)
         acc[ids] = d["part"]["acc"]
     return acc
+
+
+def run_reference_pm(pos, box, nside, mass, split=-1.0, workdir=None, timeout=3600):
+    """The reference's particle-mesh force (partmesh_thread, src/partmesh.c:18-796, compiled unmodified; its Fortran
+    convolution restated in C, oracle/ref_shim/ref_pm_harness.c) on one rank.  Returns {"acc_pm": (n, 3) in input
+    order, "density", "potential": (nside,)*3 -- the convolution's input and output --, "sec"}."""
+    if not os.path.exists(REF_EXE_PM):
+        raise RuntimeError("oracle/_ref/ref_pm is not built (run `make -C oracle ref` where /root/reference exists)")
+    pos = np.ascontiguousarray(pos, dtype=np.float64)
+    n = pos.shape[0]
+    with tempfile.TemporaryDirectory(dir=workdir) as td:
+        pfile = os.path.join(td, "params.txt")
+        with open(pfile, "w") as f:
+            f.write(f"NPART_TOTAL {n}\nBOXSIZE {float(box)!r}\nNSIDE {int(nside)}\nMASS {float(mass)!r}\nSPLIT {float(split)!r}\n")
+        xfile = os.path.join(td, "pos.f64")
+        pos.tofile(xfile)
+        res = subprocess.run([REF_EXE_PM, pfile, xfile, os.path.join(td, "out.bin")], env=dict(os.environ, PN_SHIM_NP="1"), cwd=td,
+                             capture_output=True, text=True, timeout=timeout)
+        if res.returncode != 0:
+            raise RuntimeError(f"ref_pm failed rc={res.returncode}\n{res.stdout[-2000:]}\n{res.stderr[-2000:]}")
+        r = _read_records(os.path.join(td, "out.bin"))
+    return {"acc_pm": np.frombuffer(r["acc_pm"][0], "f8").reshape(n, 3).copy(),
+            "density": np.frombuffer(r["density"][0], "f8").reshape(nside, nside, nside).copy(),
+            "potential": np.frombuffer(r["potential"][0], "f8").reshape(nside, nside, nside).copy(),
+            "sec": float(np.frombuffer(r["timing"][0], "f8")[0])}

@@ -158,6 +158,7 @@ struct pn2_ctx {
     bool own_comm = false;
     struct LetState *let = nullptr;
     struct MigState *mig = nullptr;     // domain decomposition (pn2_migrate.cu)
+    struct PmState *pm = nullptr;       // particle-mesh long-range force (pn2_pm.cu)
     DBuf<double> rec_pos, rec_acc;      // packed positions / accelerations of pn2_force_step_records
     DBuf<double> stage_in, stage_out;   // device staging of pn2_force_step's host positions / accelerations
     std::vector<pn2_domain> all_dom;
@@ -186,6 +187,7 @@ int pn2_let_exchange_nccl(pn2_ctx *h);
 int pn2_let_unpack(pn2_ctx *h);
 void pn2_let_release(pn2_ctx *h);
 void pn2_migrate_release(pn2_ctx *h);
+void pn2_pm_release(pn2_ctx *h);
 void pn2_comm_release(pn2_ctx *h);
 int pn2_step_begin(pn2_ctx *h, const double *d_pos, int n, const pn2_domain *dom);
 int pn2_step_finish(pn2_ctx *h, double *d_acc);

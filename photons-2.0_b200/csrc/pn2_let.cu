@@ -30,7 +30,7 @@ bool nccl_load() {
 #define BIND(field, sym) *(void **)(&g_nccl.field) = dlsym(hd, sym); if (!g_nccl.field) { pn2_set_error("pn2: libnccl lacks %s", sym); return false; }
     BIND(GetUniqueId, "ncclGetUniqueId") BIND(CommInitRank, "ncclCommInitRank") BIND(CommDestroy, "ncclCommDestroy")
     BIND(Send, "ncclSend") BIND(Recv, "ncclRecv") BIND(GroupStart, "ncclGroupStart") BIND(GroupEnd, "ncclGroupEnd")
-    BIND(GetErrorString, "ncclGetErrorString")
+    BIND(GetErrorString, "ncclGetErrorString") BIND(AllReduce, "ncclAllReduce")
 #undef BIND
     g_nccl.ok = true;
     return true;

@@ -14,6 +14,7 @@ void pn2_modeb_release(pn2_ctx *h) {
     for (int i = 0; i < 10; i++) if (h->ev[i]) { cudaEventDestroy(h->ev[i]); h->ev[i] = nullptr; }
     pn2_let_release(h);
     pn2_migrate_release(h);
+    pn2_pm_release(h);
     pn2_comm_release(h);
 }
 

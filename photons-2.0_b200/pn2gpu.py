@@ -34,7 +34,9 @@ EXPORTS = ["pn2_create", "pn2_destroy", "pn2_set_params", "pn2_sync", "pn2_last_
            "pn2_get_timings", "pn2_launch_count", "pn2_timer_start", "pn2_timer_stop", "pn2_comm_unique_id",
            "pn2_comm_init_rank", "pn2_step_begin", "pn2_exchange_local", "pn2_step_finish", "pn2_domain_owner_device",
            "pn2_migrate_begin", "pn2_migrate_exchange_nccl", "pn2_migrate_exchange_local", "pn2_migrate_result",
-           "pn2_migrate_device", "pn2_migrate_fetch", "pn2_kick_device", "pn2_drift_device", "pn2_force_step_records"]
+           "pn2_migrate_device", "pn2_migrate_fetch", "pn2_kick_device", "pn2_drift_device", "pn2_force_step_records",
+           "pn2_pm_force_device", "pn2_pm_force_records", "pn2_pm_begin", "pn2_pm_reduce_nccl", "pn2_pm_reduce_local",
+           "pn2_pm_finish", "pn2_pm_get_mesh", "pn2_pm_get_timings"]
 
 
 class Pn2Error(RuntimeError):
@@ -141,6 +143,14 @@ def lib():
     L.pn2_kick_device.argtypes = [vp, vp, C.c_int, C.c_double, C.c_int]
     L.pn2_drift_device.argtypes = [vp, vp, C.c_int, C.c_double, C.c_double]
     L.pn2_force_step_records.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(Domain)]
+    L.pn2_pm_force_device.argtypes = [vp, vp, C.c_int, C.c_int, vp]
+    L.pn2_pm_force_records.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.pn2_pm_begin.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.pn2_pm_reduce_nccl.argtypes = [vp]
+    L.pn2_pm_reduce_local.argtypes = [C.POINTER(vp), C.c_int]
+    L.pn2_pm_finish.argtypes = [vp, vp]
+    L.pn2_pm_get_mesh.argtypes = [vp, vp]
+    L.pn2_pm_get_timings.argtypes = [vp, dp]
     L.pn2_timer_start.argtypes = [vp, C.c_int]
     L.pn2_timer_stop.argtypes = [vp, C.c_int, dp]
     L.pn2_launch_count.argtypes = [vp]
@@ -174,6 +184,7 @@ class Context:
         self.h = C.c_void_p()
         self.params = params
         self.nranks = 1
+        self._device = device
         _ck(lib().pn2_create(C.byref(self.h), device, C.byref(params)))
 
     def close(self):
@@ -373,6 +384,42 @@ class Context:
         _ck(lib().pn2_force_step_records(self.h, d_rec_ptr, rec_doubles, acc_offset, n, C.byref(domain)))
         self.n = n
 
+    # ---- PM long-range force (src/partmesh.c:18-796, src/conv.f90:128-247) ----
+    def pm_force_device(self, d_pos_ptr, n, nside, d_acc_pm_ptr):
+        """partmesh_thread on the device: packed device positions -> acc_pm (caller order); NCCL all-reduce of the mesh when nranks > 1."""
+        _ck(lib().pn2_pm_force_device(self.h, d_pos_ptr, n, nside, d_acc_pm_ptr))
+
+    def pm_force_records(self, d_rec_ptr, rec_doubles, n, nside, acc_pm_offset=9):
+        _ck(lib().pn2_pm_force_records(self.h, d_rec_ptr, rec_doubles, acc_pm_offset, n, nside))
+
+    def pm_force(self, pos, nside):
+        """Host convenience: pos (n,3) float64 -> acc_pm (n,3)."""
+        import torch
+        t = torch.from_numpy(np.ascontiguousarray(pos, np.float64)).cuda(self.device_index())
+        a = torch.zeros_like(t)
+        self.pm_force_device(t.data_ptr(), t.shape[0], nside, a.data_ptr())
+        self.sync()
+        return a.cpu().numpy()
+
+    def device_index(self):
+        return getattr(self, "_device", 0)
+
+    def pm_begin(self, d_pos_ptr, n, nside):
+        _ck(lib().pn2_pm_begin(self.h, d_pos_ptr, n, nside))
+
+    def pm_finish(self, d_acc_pm_ptr):
+        _ck(lib().pn2_pm_finish(self.h, d_acc_pm_ptr))
+
+    def pm_mesh(self, nside):
+        m = np.zeros((nside, nside, nside))
+        _ck(lib().pn2_pm_get_mesh(self.h, m.ctypes.data))
+        return m
+
+    def pm_timings(self):
+        t = np.zeros(4)
+        _ck(lib().pn2_pm_get_timings(self.h, t.ctypes.data_as(C.POINTER(C.c_double))))
+        return dict(zip(["deposit", "reduce", "fft_green", "gather"], t))
+
     def step_info(self):
         s = StepInfo()
         _ck(lib().pn2_get_step_info(self.h, C.byref(s)))
@@ -447,6 +494,12 @@ def migrate_exchange_local(ctxs):
     """The all-to-all-v of the records between contexts of this process (after migrate_begin on every rank)."""
     arr = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
     _ck(lib().pn2_migrate_exchange_local(arr, len(ctxs)))
+
+
+def pm_reduce_local(ctxs):
+    """Sum of the density meshes of the contexts of this process (after pm_begin on every rank)."""
+    arr = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+    _ck(lib().pn2_pm_reduce_local(arr, len(ctxs)))
 
 
 def exchange_local(ctxs):
