@@ -214,6 +214,12 @@ int pn2_drift_device(pn2_ctx *h, double *d_body, int n, double dd, double box);
  * Same result as pn2_force_step_device on the packed positions. */
 int pn2_force_step_records(pn2_ctx *h, double *d_rec, int rec_doubles, int acc_offset, int n, const pn2_domain *dom);
 
+/* ---- Gadget-2 snapshot blocks <-> device Body records (src/snapshot.c:211-293, 397-503) --------------
+ * d_pos32 / d_vel32: the file's float32 blocks [n][3] in device memory (vel32 = v / a^1.5; may be NULL on read: vel = 0);
+ * gdt2unit = a^1.5 = (1 / (1 + redshift))^1.5 (:261, :469).  Same roundings as the reference's reader and writer. */
+int pn2_snapshot_to_body_device(pn2_ctx *h, const float *d_pos32, const float *d_vel32, int n, double gdt2unit, double *d_body);
+int pn2_body_to_snapshot_device(pn2_ctx *h, const double *d_body, int n, double gdt2unit, float *d_pos32, float *d_vel32);
+
 /* ---- particle-mesh long-range force on the device (src/partmesh.c:18-796, src/conv.f90:128-247) ------
  * partmesh_thread: CIC deposit of the particles on the NSIDE^3 mesh (:98-178), the mesh all-to-all into the FFT pencils
  * (:188-352) and back (:430-470), convolution (conv.f90: FFT, Green function pref exp(-k^2 rs^2) sinc^-4 / k^2, inverse

@@ -87,3 +87,50 @@ extern "C" int pn2_force_step_records(pn2_ctx *h, double *d_rec, int rec_doubles
     KERNEL_CHECK();
     return PN2_OK;
 }
+
+// ---- Gadget-2 snapshot blocks <-> device Body records (src/snapshot.c:211-293, 397-503) ----
+// The file holds float32 pos[N][3] and float32 vel[N][3] = v / a^1.5.  The reader widens the positions and multiplies the
+// widened velocities by gdt2unit = a^1.5 (:261-276); the writer stores (float)pos and (float)((float)vel / gdt2unit)
+// (:465-480).  The blocks are uploaded as they are in the file (half the bytes of the records) and converted on the device.
+__global__ void snap_to_body_kernel(long n, const float *__restrict__ pos32, const float *__restrict__ vel32, double gdt2unit,
+                                    double *__restrict__ body) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double *b = body + (size_t)i * BODY_DOUBLES;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        b[d] = (double)pos32[3 * i + d];
+        b[3 + d] = 0.0;
+        b[6 + d] = vel32 ? __dmul_rn((double)vel32[3 * i + d], gdt2unit) : 0.0;
+        b[9 + d] = 0.0;
+    }
+}
+__global__ void body_to_snap_kernel(long n, const double *__restrict__ body, double gdt2unit, float *__restrict__ pos32,
+                                    float *__restrict__ vel32) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double *b = body + (size_t)i * BODY_DOUBLES;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        pos32[3 * i + d] = (float)b[d];
+        vel32[3 * i + d] = (float)__ddiv_rn((double)(float)b[6 + d], gdt2unit);
+    }
+}
+extern "C" int pn2_snapshot_to_body_device(pn2_ctx *h, const float *d_pos32, const float *d_vel32, int n, double gdt2unit, double *d_body) {
+    if (!h || n < 0 || (n > 0 && (!d_pos32 || !d_body))) { pn2_set_error("pn2_snapshot_to_body_device: bad argument"); return PN2_ERR_ARG; }
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (n == 0) return PN2_OK;
+    snap_to_body_kernel<<<(unsigned)((n + 255L) / 256), 256, 0, h->stream>>>(n, d_pos32, d_vel32, gdt2unit, d_body);
+    h->launches++;
+    KERNEL_CHECK();
+    return PN2_OK;
+}
+extern "C" int pn2_body_to_snapshot_device(pn2_ctx *h, const double *d_body, int n, double gdt2unit, float *d_pos32, float *d_vel32) {
+    if (!h || n < 0 || (n > 0 && (!d_pos32 || !d_vel32 || !d_body)) || !(gdt2unit > 0.0)) { pn2_set_error("pn2_body_to_snapshot_device: bad argument"); return PN2_ERR_ARG; }
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (n == 0) return PN2_OK;
+    body_to_snap_kernel<<<(unsigned)((n + 255L) / 256), 256, 0, h->stream>>>(n, d_body, gdt2unit, d_pos32, d_vel32);
+    h->launches++;
+    KERNEL_CHECK();
+    return PN2_OK;
+}

@@ -36,7 +36,7 @@ EXPORTS = ["pn2_create", "pn2_destroy", "pn2_set_params", "pn2_sync", "pn2_last_
            "pn2_migrate_begin", "pn2_migrate_exchange_nccl", "pn2_migrate_exchange_local", "pn2_migrate_result",
            "pn2_migrate_device", "pn2_migrate_fetch", "pn2_kick_device", "pn2_drift_device", "pn2_force_step_records",
            "pn2_pm_force_device", "pn2_pm_force_records", "pn2_pm_begin", "pn2_pm_reduce_nccl", "pn2_pm_reduce_local",
-           "pn2_pm_finish", "pn2_pm_get_mesh", "pn2_pm_get_timings"]
+           "pn2_pm_finish", "pn2_pm_get_mesh", "pn2_pm_get_timings", "pn2_snapshot_to_body_device", "pn2_body_to_snapshot_device"]
 
 
 class Pn2Error(RuntimeError):
@@ -151,6 +151,8 @@ def lib():
     L.pn2_pm_finish.argtypes = [vp, vp]
     L.pn2_pm_get_mesh.argtypes = [vp, vp]
     L.pn2_pm_get_timings.argtypes = [vp, dp]
+    L.pn2_snapshot_to_body_device.argtypes = [vp, vp, vp, C.c_int, C.c_double, vp]
+    L.pn2_body_to_snapshot_device.argtypes = [vp, vp, C.c_int, C.c_double, vp, vp]
     L.pn2_timer_start.argtypes = [vp, C.c_int]
     L.pn2_timer_stop.argtypes = [vp, C.c_int, dp]
     L.pn2_launch_count.argtypes = [vp]
