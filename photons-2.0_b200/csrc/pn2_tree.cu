@@ -268,6 +268,162 @@ __global__ void scatter_kernel(int n, const uint4 *__restrict__ pay, const int *
     q_o[np] = next_dir == 0 ? p.x : (next_dir == 1 ? p.y : p.z);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Top levels without moving the particles (deferred partition)
+// ------------------------------------------------------------------------------------------------
+// While the nodes are large the per-level stable partition is pure bookkeeping: a particle's final slot only depends on
+// the node it ends up in and on its Morton rank.  The top levels therefore leave the payload where the Morton sort put
+// it and only relabel: seg[i] = child slot 2 (node - node0) + side, the children's counts and coordinate sums (of the
+// NEXT split direction: the next level needs no separate sum pass) accumulated per block in a small shared-memory
+// table and flushed with integer atomics (exact, order-independent, as in nodesum_kernel).  24 bytes of traffic per
+// particle and level instead of ~74.  One stable radix sort on the node start positions then makes the nodes contiguous
+// in Morton order -- exactly the state the level-by-level partitions would have reached -- and the remaining levels
+// run as before.
+#define TOP_ITEMS 4
+#define TOP_TAB 64
+__device__ __forceinline__ unsigned pay_dir(const uint4 &p, int dir) { return dir == 0 ? p.x : (dir == 1 ? p.y : p.z); }
+
+__global__ void __launch_bounds__(TB) top_level_kernel(int n, const uint4 *__restrict__ pay, int *__restrict__ seg,
+                                                       const int *__restrict__ slot2id, int node0, const int *__restrict__ n_count,
+                                                       const unsigned long long *__restrict__ n_sum, int dir, int ndir,
+                                                       unsigned long long *__restrict__ csum, unsigned *__restrict__ ccnt) {
+    __shared__ int t_key[TOP_TAB];
+    __shared__ unsigned long long t_sum[TOP_TAB];
+    __shared__ unsigned t_cnt[TOP_TAB];
+    if (threadIdx.x < TOP_TAB) { t_key[threadIdx.x] = -1; t_sum[threadIdx.x] = 0ULL; t_cnt[threadIdx.x] = 0u; }
+    __syncthreads();
+    auto table_add = [&](int key, unsigned long long sv, unsigned cv) {
+        unsigned hh = ((unsigned)key * 2654435761u) >> 26;                  // 6 bits
+        for (int probe = 0; probe < 8; probe++) {
+            const int at = (int)((hh + probe) & (TOP_TAB - 1));
+            const int old = atomicCAS(&t_key[at], -1, key);
+            if (old == -1 || old == key) { atomicAdd(&t_sum[at], sv); atomicAdd(&t_cnt[at], cv); return; }
+        }
+        atomicAdd(&csum[key], sv); atomicAdd(&ccnt[key], cv);              // table full: straight to global memory
+    };
+    const long base = ((long)blockIdx.x * TB + threadIdx.x) * TOP_ITEMS;
+    int cur = -1;
+    unsigned long long cs = 0ULL;
+    unsigned cc = 0u;
+#pragma unroll
+    for (int k = 0; k < TOP_ITEMS; k++) {
+        const long i = base + k;
+        if (i >= n) break;
+        int s = seg[i];
+        if (s >= 0 && slot2id) s = slot2id[s];                              // the slot of the previous level -> node id / leaf code
+        if (s < 0) { seg[i] = s; continue; }                                // in a leaf: final
+        const uint4 p = pay[i];
+        const int c = n_count[s];
+        const unsigned long long sm = n_sum[s];
+        const int fl = (c < 2) ? 1 : (((unsigned long long)pay_dir(p, dir) * (unsigned long long)c > sm) ? 1 : 0);   // src/fmm.c:33-36, 60-72
+        const int slot = 2 * (s - node0) + fl;
+        seg[i] = slot;
+        if (slot != cur) {
+            if (cur >= 0) table_add(cur, cs, cc);
+            cur = slot; cs = 0ULL; cc = 0u;
+        }
+        cs += pay_dir(p, ndir);
+        cc++;
+    }
+    // the thread's last run: lanes with the same slot are merged first (the common case: the whole warp)
+    const unsigned peers = __match_any_sync(0xffffffffu, cur);
+    const unsigned lo = __reduce_add_sync(peers, (unsigned)(cs & 0xffffffULL));
+    const unsigned hi = __reduce_add_sync(peers, (unsigned)(cs >> 24));
+    const unsigned ct = __reduce_add_sync(peers, cc);
+    if (cur >= 0 && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) table_add(cur, (unsigned long long)lo + ((unsigned long long)hi << 24), ct);
+    __syncthreads();
+    if (threadIdx.x < TOP_TAB && t_key[threadIdx.x] >= 0) {
+        atomicAdd(&csum[t_key[threadIdx.x]], t_sum[threadIdx.x]);
+        atomicAdd(&ccnt[t_key[threadIdx.x]], t_cnt[threadIdx.x]);
+    }
+}
+
+__global__ void childcount_top_kernel(int cnt, const unsigned *__restrict__ ccnt, int maxleaf, unsigned long long *__restrict__ cc) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > cnt) return;
+    unsigned long long v = 0;
+    if (k < cnt) {
+        unsigned nl = ((int)ccnt[2 * k] <= maxleaf) + ((int)ccnt[2 * k + 1] <= maxleaf);
+        v = (unsigned long long)nl | ((unsigned long long)(2 - nl) << 32);
+    }
+    cc[k] = v;
+}
+
+// children_kernel for a deferred level: the counts come from ccnt, a node child starts with its coordinate sum, and
+// slot2id tells the next level (and the final sort) where every slot went
+__global__ void children_top_kernel(int cnt, int node0, int next_node0, int leaf0, int dir, int depth, int maxleaf,
+                                    int *__restrict__ n_start, int *__restrict__ n_count, int *__restrict__ n_son,
+                                    int *__restrict__ n_depth, double *__restrict__ n_box, const double *__restrict__ n_split,
+                                    int *__restrict__ l_start, int *__restrict__ l_count, double *__restrict__ l_box,
+                                    const unsigned long long *__restrict__ csum, const unsigned *__restrict__ ccnt,
+                                    const unsigned long long *__restrict__ ccs, int node_cap, int leaf_cap, int *__restrict__ scal,
+                                    unsigned long long *__restrict__ n_sum, int *__restrict__ slot2id) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= cnt) return;
+    int nd = node0 + k;
+    int a = n_start[nd];
+    int cn[2] = {(int)ccnt[2 * k], (int)ccnt[2 * k + 1]};
+    int st[2] = {a, a + cn[0]};
+    unsigned long long off = ccs[k];
+    int li = leaf0 + (int)(off & 0xffffffffULL), ni = next_node0 + (int)(off >> 32);
+    double box[6];
+#pragma unroll
+    for (int d = 0; d < 6; d++) box[d] = n_box[6 * (size_t)nd + d];
+    double sp = n_split[nd];
+    for (int s = 0; s < 2; s++) {
+        double cb[6];
+#pragma unroll
+        for (int d = 0; d < 6; d++) cb[d] = box[d];
+        if (s == 0) cb[3 + dir] = sp; else cb[dir] = sp;          // center_kdtree, src/fmm.c:140-176
+        if (cn[s] <= maxleaf) {
+            if (li < leaf_cap) {
+                l_start[li] = st[s]; l_count[li] = cn[s];
+#pragma unroll
+                for (int d = 0; d < 6; d++) l_box[6 * (size_t)li + d] = cb[d];
+            } else atomicExch(&scal[3], 1);
+            n_son[2 * (size_t)nd + s] = -(li + 2);
+            slot2id[2 * k + s] = -(li + 2);
+            li++;
+        } else {
+            if (ni < node_cap) {
+                n_start[ni] = st[s]; n_count[ni] = cn[s]; n_depth[ni] = depth + 1; n_sum[ni] = csum[2 * k + s];
+#pragma unroll
+                for (int d = 0; d < 6; d++) n_box[6 * (size_t)ni + d] = cb[d];
+            } else atomicExch(&scal[3], 1);
+            n_son[2 * (size_t)nd + s] = ni;
+            slot2id[2 * k + s] = ni;
+            ni++;
+        }
+    }
+    if (k == cnt - 1) {
+        unsigned long long tot = ccs[cnt];
+        scal[0] = (int)(tot >> 32);
+        scal[1] = leaf0 + (int)(tot & 0xffffffffULL);
+    }
+}
+
+// end of the deferred phase: the sort key of a particle = the start position of its node / leaf
+__global__ void top_finish_kernel(int n, const int *__restrict__ seg, const int *__restrict__ slot2id, const int *__restrict__ n_start,
+                                  const int *__restrict__ l_start, unsigned *__restrict__ key, int *__restrict__ seg_o, int *__restrict__ iota) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int s = seg[i];
+    if (s >= 0 && slot2id) s = slot2id[s];
+    key[i] = (unsigned)(s >= 0 ? n_start[s] : l_start[-(s + 2)]);
+    seg_o[i] = s >= 0 ? s : -1;
+    iota[i] = i;
+}
+__global__ void top_gather_kernel(int n, const int *__restrict__ idx, const uint4 *__restrict__ pay, const int *__restrict__ seg, int dir,
+                                  uint4 *__restrict__ pay_o, int *__restrict__ seg_o, unsigned *__restrict__ q_o) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int i = idx[j];
+    const uint4 p = pay[i];
+    pay_o[j] = p;
+    seg_o[j] = seg[i];
+    q_o[j] = pay_dir(p, dir);
+}
+
 // tree-order positions and caller indices from the final payload
 __global__ void finalize_particles_kernel(int n, const uint4 *__restrict__ pay, const double *__restrict__ pos_in,
                                           double *__restrict__ pos, int *__restrict__ order) {
@@ -360,9 +516,12 @@ static int tree_build_once(pn2_ctx *h, const double *d_pos_in, int n, const pn2_
     cub::DeviceRadixSort::SortPairs(nullptr, tb, h->b_q.p, h->b_key2.p, h->b_idx2.p, h->order.p, n, 0, 63, st);
     cub::DeviceScan::ExclusiveSum(nullptr, tb3, flag_it, h->b_f.p, n + 1, st);
     cub::DeviceScan::ExclusiveSum(nullptr, tb4, h->b_q.p, h->b_q.p, cap + 1, st);
+    size_t tb5 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb5, h->b_qc.p, h->b_qc2.p, h->b_idx2.p, h->order.p, n, 0, 32, st);
     size_t need = tb;
     if (tb3 > need) need = tb3;
     if (tb4 > need) need = tb4;
+    if (tb5 > need) need = tb5;
     PN2_TRY(h->tmp.ensure(need + 16));
     cub::DeviceRadixSort::SortPairs(h->tmp.p, tb, h->b_q.p, h->b_key2.p, h->b_idx2.p, h->order.p, n, 0, 63, st);
     gather_pay_kernel<<<nb(n), TB, 0, st>>>(n, h->b_pay2.p, h->order.p, dom->direct0 % 3, h->b_pay.p, h->b_qc.p, h->b_seg.p);
@@ -388,6 +547,55 @@ static int tree_build_once(pn2_ctx *h, const double *d_pos_in, int n, const pn2_
     int *sg = h->b_seg.p, *so = h->b_seg2.p;
     int node0 = 0, cnt = 1, nleaf = 0, level = 0;
     std::vector<int> level_off(1, 0);
+
+    // ---- deferred top levels (see top_level_kernel): while nodes hold more than ~top_target particles on average ----
+    int ktop = 0;
+    while (((long)n >> (ktop + 1)) >= h->tree_top_target) ktop++;
+    if (ktop > 0) {
+        nodesum_kernel<<<nb(((long)n + NS_ITEMS - 1) / NS_ITEMS), TB, 0, st>>>(n, qc, sg, h->n_sum.p);      // the root's sum
+        h->launches++;
+        unsigned long long *csum = h->b_key2.p;
+        unsigned *ccnt = reinterpret_cast<unsigned *>(h->b_f.p);
+        int *s2i_prev = nullptr, *s2i = h->b_idx2.p, *s2i_other = h->b_seg2.p;
+        while (cnt > 0 && level < ktop) {
+            const int dir = (dom->direct0 + level) % 3;
+            split_kernel<<<nb(cnt), TB, 0, st>>>(cnt, node0, h->n_count.p, h->n_sum.p, dom->lo[dir], invS, h->n_split.p);
+            CUDA_TRY(cudaMemsetAsync(csum, 0, 2 * (size_t)cnt * sizeof(unsigned long long), st));
+            CUDA_TRY(cudaMemsetAsync(ccnt, 0, 2 * (size_t)cnt * sizeof(unsigned), st));
+            top_level_kernel<<<nb(((long)n + TOP_ITEMS - 1) / TOP_ITEMS), TB, 0, st>>>(n, pc, sg, s2i_prev, node0, h->n_count.p, h->n_sum.p, dir,
+                                                                                   (dir + 1) % 3, csum, ccnt);
+            childcount_top_kernel<<<nb(cnt + 1), TB, 0, st>>>(cnt, ccnt, maxleaf, h->b_q.p);
+            cub::DeviceScan::ExclusiveSum(h->tmp.p, tb4, h->b_q.p, h->b_q.p, cnt + 1, st);
+            children_top_kernel<<<nb(cnt), TB, 0, st>>>(cnt, node0, node0 + cnt, nleaf, dir, level, maxleaf, h->n_start.p, h->n_count.p,
+                                                        h->n_son.p, h->n_depth.p, h->n_box.p, h->n_split.p, h->l_start.p, h->l_count.p,
+                                                        h->l_box.p, csum, ccnt, h->b_q.p, cap, cap, h->b_scal.p, h->n_sum.p, s2i);
+            h->launches += 5;
+            int hs[4];
+            CUDA_TRY(cudaMemcpyAsync(hs, h->b_scal.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            if (hs[3]) { *overflow = true; return PN2_OK; }
+            s2i_prev = s2i; std::swap(s2i, s2i_other);
+            node0 += cnt;
+            level_off.push_back(node0);
+            cnt = hs[0];
+            nleaf = hs[1];
+            level++;
+        }
+        // one stable sort on the start positions: nodes (and finished leaves) become contiguous, Morton order inside
+        unsigned *key = h->b_qc.p, *key_s = h->b_qc2.p;
+        int *seg_m = h->b_f.p;                                   // the count table is consumed
+        int *iota = s2i;                                         // the slot table that is NOT the live one
+        top_finish_kernel<<<nb(n), TB, 0, st>>>(n, sg, s2i_prev, h->n_start.p, h->l_start.p, key, seg_m, iota);
+        int bits = 1;
+        while ((1L << bits) < (long)n && bits < 32) bits++;
+        cub::DeviceRadixSort::SortPairs(h->tmp.p, tb5, key, key_s, iota, h->order.p, n, 0, bits, st);
+        const int dirk = (dom->direct0 + level) % 3;
+        top_gather_kernel<<<nb(n), TB, 0, st>>>(n, h->order.p, pc, seg_m, dirk, po, sg, key);      // key (b_qc) is free again: the level's q
+        h->launches += 3;
+        std::swap(pc, po);
+        qc = key; qo = key_s;
+        if (cnt > 0) CUDA_TRY(cudaMemsetAsync(h->n_sum.p + node0, 0, (size_t)cnt * sizeof(unsigned long long), st));
+    }
     while (cnt > 0) {
         if (level > 200) { pn2_set_error("pn2: tree deeper than 200 levels (more than MAXLEAF coincident particles?)"); return PN2_ERR_ARG; }
         int dir = (dom->direct0 + level) % 3;

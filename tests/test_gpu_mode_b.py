@@ -197,3 +197,30 @@ def test_merger_ic_vs_reference(pn2, oracle, nranks):
         assert sum(i["n_interactions"] for i in infos) == int(g["nint_local"].sum() + g["p2p_count_remote"].sum())
         assert sum(i["n_m2l_pairs"] for i in infos) == int(g["walk_m2l_count"].sum())
         assert err < TOL[precision] and err < {2: 1e-10, 0: 2e-9, 1: 3e-5}[precision]
+
+
+@pytest.mark.parametrize("target", [2, 16, 200, 1 << 20])
+def test_tree_deferred_top_levels_bit_exact(pn2, oracle, demo_pos, target, monkeypatch):
+    """The tree build's deferred top levels (top_level_kernel: particles relabelled in place, one radix sort at the
+    switch) must give the tree of the level-by-level partitions, whatever the switch depth: PN2_TREE_TOP_TARGET = 2
+    defers every level, 16 / 200 switch inside the tree (also where leaves already exist), 2^20 defers none.  Checked
+    bit for bit against the oracle's restatement of the device builder (ids, order, boxes, sons) on the demo IC
+    (uniform), a clustered ragged set and a rank-2 domain box with direct0 = 1."""
+    monkeypatch.setenv("PN2_TREE_TOP_TARGET", str(target))
+    rng = np.random.default_rng(11)
+    box = 1000.0
+    blob = np.concatenate([rng.normal(500, 15, (3000, 3)), rng.normal(200, 4, (1500, 3)), rng.random((1500, 3)) * box])
+    blob = np.mod(blob, box)
+    blob[:64, 0] = 123.456
+    dbox = float(load_golden("demo_ns32_np1.npz")["box"])
+    half = demo_pos[demo_pos[:, 0] > 0.5 * dbox]
+    cases = [(demo_pos, dbox, 8, [0, 0, 0], [dbox] * 3, 0), (blob, box, 8, [0, 0, 0], [box] * 3, 0), (blob, box, 32, [0, 0, 0], [box] * 3, 0),
+             (half, dbox, 8, [0.5 * dbox, 0, 0], [dbox] * 3, 1)]
+    for pos, bx, maxleaf, lo, hi, d0 in cases:
+        prm_o = oracle.make_params(bx, 16, len(pos), 1.0, maxleaf=maxleaf, theta=0.5)
+        tb = oracle.TreeB(pos, maxleaf, lo, hi, direct0=d0)
+        ctx = make_ctx(pn2, prm_o, 1)
+        acc = ctx.force_step(pos, pn2.make_domain(lo, hi, d0))
+        check_tree(ctx, tb)
+        assert np.isfinite(acc).all()
+        ctx.close()
