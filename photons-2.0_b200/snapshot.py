@@ -112,8 +112,8 @@ def load_body_device(ctx, path, n_start=0, n_count=None):
     pos, vel, head, unit = read_blocks(path, n_start, n_count)
     n = pos.shape[0]
     dev = torch.device("cuda", ctx.device_index())
-    hp = torch.from_numpy(np.ascontiguousarray(pos)).pin_memory()
-    hv = torch.from_numpy(np.ascontiguousarray(vel)).pin_memory()
+    hp = torch.from_numpy(np.array(pos)).pin_memory()            # np.frombuffer views are read-only: copy
+    hv = torch.from_numpy(np.array(vel)).pin_memory()
     dp, dv = hp.to(dev, non_blocking=True), hv.to(dev, non_blocking=True)
     body = torch.empty((n, 12), dtype=torch.float64, device=dev)
     torch.cuda.synchronize(dev)

@@ -77,7 +77,8 @@ def test_snapshot_to_device_records_and_back(tmp_path):
     g = np.load(os.path.join(GOLD, "snapshot_golden.npz"))
     path = os.path.join(GOLD, "ref_written_256.gdt2")
     pos, vel, head = snapshot.read_gadget2(path)
-    ctx = pn2gpu.Context(pn2gpu.make_params(float(g["BOXSIZE"]), 32, 256, float(g["MASSPART"])))
+    # 256 particles in the whole box: leaves far wider than the split scale -> FP64 mode (the FP32 tile layout refuses them)
+    ctx = pn2gpu.Context(pn2gpu.make_params(float(g["BOXSIZE"]), 32, 256, float(g["MASSPART"]), precision=pn2gpu.FP64))
     body, head_d = snapshot.load_body_device(ctx, path)
     hb = body.cpu().numpy()
     np.testing.assert_array_equal(hb, snapshot.to_body(pos, vel))
