@@ -44,9 +44,15 @@ def parse():
     ap.add_argument("--theta", type=float, default=0.4)
     ap.add_argument("--disp-rms", type=float, default=0.3, help="rms Zel'dovich displacement in grid spacings")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
+    ap.add_argument("--ic", default="lcdm", choices=["lcdm", "poisson", "merger"],
+                    help="lcdm: grid + Zel'dovich displacements (default); poisson: uniform random (the reference's ic_uniform); "
+                         "merger: the reference's demo/ic_merger.gdt2 (non-periodic Newtonian build, M2L-heavy; 1 GPU)")
     ap.add_argument("--cpu-sample-side", type=int, default=96, help="particles per dimension of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--rebalance", type=int, default=0,
+                    help="after the timed region (N > 1): this many iterations of the reference's load-balance loop -- DTIME_FRACTION from the "
+                         "ranks' list sizes, determine_split_domtree, particle migration, force step -- reported as `rebalance`")
     return ap.parse_args()
 
 
@@ -218,8 +224,15 @@ def run_reference_arm(args):
 
 def workload_config(args, ngpu):
     nside = args.nside or args.npart_side
-    return {"workload": f"synthetic LCDM-like {args.npart_side}^3 particles, periodic box {100000.0:g} kpc/h, NSIDE {nside}, "
-                        f"Zel'dovich displacement rms {args.disp_rms} grid spacings, seed 12345",
+    if args.ic == "merger":
+        return {"workload": "the reference's demo/ic_merger.gdt2 (60000 particles, two clustered haloes) shifted into a BOX 400, non-periodic "
+                            "Newtonian build (no -DPERIODIC_CONDITION -DLONGSHORT), NSIDE 8", "npart": 60000, "nside": 8, "maxleaf": args.maxleaf,
+                "theta": args.theta, "precision_mode": args.precision, "parallelism": f"domains{ngpu}", "cache": "fits L2"}
+    what = (f"synthetic LCDM-like {args.npart_side}^3 particles, periodic box {100000.0:g} kpc/h, NSIDE {nside}, "
+            f"Zel'dovich displacement rms {args.disp_rms} grid spacings, seed 12345") if args.ic == "lcdm" else \
+           (f"Poisson (uniform random, the reference's ic_uniform: src/initial.c:558-618) {args.npart_side}^3 particles, periodic box "
+            f"{100000.0:g} kpc/h, NSIDE {nside}, seed 378412")
+    return {"workload": what,
             "npart": args.npart_side ** 3, "nside": nside, "maxleaf": args.maxleaf, "theta": args.theta,
             "precision_mode": args.precision, "parallelism": f"domains{ngpu}",
             "cache": "inputs (positions, tree, multipoles: several GB) exceed the 126 MB L2; no explicit flush"}
@@ -251,11 +264,26 @@ def main():
     ntot = args.npart_side ** 3
     mass = synthetic.particle_mass(ntot)
     precision = pn2gpu.FP32 if args.precision == "fp32" else pn2gpu.FP64
-    prm = pn2gpu.make_params(synthetic.BOX, nside, ntot, mass, maxleaf=args.maxleaf, theta=args.theta, precision=precision)
+    box = synthetic.BOX
+    if args.ic == "merger":
+        if world > 1:
+            raise SystemExit("bench.py: --ic merger is a single-GPU line")
+        g = np.load(os.path.join(ROOT, "tests", "golden", "merger_open_np1.npz"))
+        mpos = np.load(os.path.join(ROOT, "tests", "golden", "merger_pos_f32.npy")).astype(np.float64) + float(g["shift"])
+        box, nside, ntot, mass = float(g["box"]), int(g["nside"]), len(mpos), float(g["mass"])
+        prm = pn2gpu.make_params(box, nside, ntot, mass, maxleaf=args.maxleaf, theta=args.theta, soft=float(g["soft"]), periodic=0, longshort=0,
+                                 precision=precision)
+    else:
+        prm = pn2gpu.make_params(box, nside, ntot, mass, maxleaf=args.maxleaf, theta=args.theta, precision=precision)
     ctx = pn2gpu.Context(prm, device=local)
 
     # ---- workload: every rank generates the same field, keeps the particles of its own domain ----
-    pos_all = synthetic.lcdm_like(args.npart_side, disp_rms=args.disp_rms, seed=12345, device=dev)
+    if args.ic == "merger":
+        pos_all = torch.from_numpy(mpos).to(dev)
+    elif args.ic == "poisson":
+        pos_all = synthetic.poisson(ntot, seed=378412, device=dev)
+    else:
+        pos_all = synthetic.lcdm_like(args.npart_side, disp_rms=args.disp_rms, seed=12345, device=dev)
     migrate = None
     if world > 1:
         # every rank starts with an arbitrary slice of the set; the particles reach the rank that owns them under the
@@ -292,7 +320,7 @@ def main():
         pos_all = None
     else:
         pos = pos_all
-        dom = pn2gpu.make_domain([0, 0, 0], [synthetic.BOX] * 3, 0)
+        dom = pn2gpu.make_domain([0, 0, 0], [box] * 3, 0)
     del pos_all
     torch.cuda.empty_cache()
     n = pos.shape[0]
@@ -313,6 +341,7 @@ def main():
         step()
     barrier()
     fma_peak = ctx.fma_peak(precision != pn2gpu.FP32)     # FFMA issue rate (FP32 mode) / DFMA issue rate (FP64 mode)
+    dfma_peak = ctx.fma_peak(True)                        # the multipole operators always run in FP64
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -374,6 +403,40 @@ def main():
                "max_abs_diff_vs_device_step_rank0": float((hacc[:m_chk].to(dev) - acc[:m_chk]).abs().max()),
                "rms_acc_rank0": float(torch.sqrt((acc[:m_chk] ** 2).sum(1).mean()))}
 
+    # ---- the reference's load-balance loop (src/photoNs.c:270-283, src/domains.c:21-160, 268-375) on the measured load ----
+    rebalance = None
+    if args.rebalance > 0 and world > 1:
+        rebalance = []
+        cur_pos, cur_n, cur_dom = pos, n, dom
+        for it in range(args.rebalance + 1):
+            if it > 0:
+                # DTIME_THIS_DOMAIN = idxP2P + idxM2L (src/fmm.c:1069); DTIME_FRACTION = this * P / total (src/photoNs.c:281)
+                inf = ctx.step_info()
+                ld = torch.zeros(world, dtype=torch.float64, device=dev)
+                ld[rank] = float(inf["n_p2p_pairs"] + inf["n_m2l_pairs"])
+                dist.all_reduce(ld)
+                load = (ld * world / (ld.sum() + 0.0001)).cpu().numpy()
+                dtree.update(load)                                       # determine_split_domtree
+                doms = dtree.boxes()
+                ctx.set_comm(rank, world, doms, None)                    # same communicator, new domain table
+                ptr, n_new = ctx.migrate_device(cur_pos.data_ptr(), 3, cur_n, dtree.splits)
+                new_pos = torch.empty((n_new, 3), dtype=torch.float64, device=dev)
+                pn2gpu._ck(pn2gpu.lib().pn2_migrate_fetch(ctx.h, new_pos.data_ptr()))
+                cur_pos, cur_n, cur_dom = new_pos, n_new, doms[rank]
+            cur_acc = torch.empty_like(cur_pos)
+            barrier()
+            ctx.timer_start(3)
+            ctx.force_step_device(cur_pos.data_ptr(), cur_n, cur_acc.data_ptr(), cur_dom)
+            ms_it = ctx.timer_stop(3)
+            inf = ctx.step_info()
+            v = torch.tensor([ms_it, float(inf["n_p2p_pairs"] + inf["n_m2l_pairs"]), float(cur_n), float(inf["n_interactions"])], dtype=torch.float64, device=dev)
+            allv = [torch.zeros_like(v) for _ in range(world)]
+            dist.all_gather(allv, v)
+            A = torch.stack(allv).cpu().numpy()
+            rebalance.append({"iter": it, "ms_max": float(A[:, 0].max()), "ms_mean": float(A[:, 0].mean()),
+                              "imbalance_pct": float(100.0 * (1.0 - A[:, 1].sum() / (world * A[:, 1].max()))),       # src/photoNs.c:284
+                              "load_max_over_mean": float(A[:, 1].max() / A[:, 1].mean()), "n_min": int(A[:, 2].min()), "n_max": int(A[:, 2].max()),
+                              "interactions_total": float(A[:, 3].sum())})
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -403,8 +466,8 @@ def main():
            "config": workload_config(args, world),
            "p2p_ginteractions_per_s": nint_total / (ms_step * 1e-3) / 1e9,
            "interactions_per_particle": nint_total / n_total,
-           "migrate": migrate, "momentum_residual": momentum_residual,
-           "phases_ms": {k: float(np.mean([p[k] for p in phase])) for k in ("tree", "upward", "frontier", "walk_p2p", "m2l", "downward", "let", "total")},
+           "migrate": migrate, "momentum_residual": momentum_residual, "rebalance": rebalance,
+           "phases_ms": {k: float(np.mean([p[k] for p in phase])) for k in ("tree", "upward", "frontier", "walk_p2p", "m2l", "m2l_kernel", "downward", "let", "total")},
            "tree": {"nleaf": info["nleaf"], "nnode": info["nnode"], "levels": info["nlevel"], "m2l_pairs": info["n_m2l_pairs"],
                     "p2p_leaf_pairs": info["n_p2p_pairs"], "walk_visits": info["n_walk_visits"],
                     "frontier_bytes": info["frontier_bytes"]},
@@ -417,7 +480,19 @@ def main():
                         "frac_executed": (23 if fp32 else 28) / OPS_PER_INTERACTION * ach / fma_peak, "traffic": traffic,
                         "hbm_peak_gbs_measured": peaks.get("hbm_gbs")},
            "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e}
-    if not args.no_cpu_baseline and world == 1:
+    # padded tiles: the kernel evaluates SW x SW lane products per leaf pair whatever the leaves hold
+    sw = 8 if args.maxleaf <= 8 else (16 if args.maxleaf <= 16 else 32)
+    lane_eff = info["n_interactions"] / max(1, info["n_p2p_pairs"] * sw * sw)
+    out["tiles"] = {"slots": sw, "particles_per_leaf": info["n"] / max(1, info["nleaf"]), "lane_efficiency_rank0": lane_eff,
+                    "note": "roofline.frac counts listed interactions; frac / lane_efficiency = what the lanes executed incl. padding slots"}
+    out["roofline"]["frac_incl_padding_lanes"] = out["roofline"]["frac"] / lane_eff if lane_eff > 0 else None
+    m2l_ms = float(np.mean([p["m2l_kernel"] for p in phase]))
+    if info["n_m2l_pairs"] > 0 and m2l_ms > 0:
+        m2l_ops = 160.0 * info["n_m2l_pairs"] / (m2l_ms * 1e-3)
+        out["m2l"] = {"pairs_rank0": info["n_m2l_pairs"], "kernel_ms": m2l_ms, "ops_per_pair": 160, "achieved_tops": m2l_ops / 1e12,
+                      "dfma_peak_tops": dfma_peak / 1e12, "frac_of_dfma_peak": m2l_ops / dfma_peak,
+                      "kernel": "m2l_warp_kernel (FP64, libm erfc / exp in the long/short build)"}
+    if not args.no_cpu_baseline and world == 1 and args.ic == "lcdm":
         cores = host_cores()
         nr = 1
         while nr * 2 <= cores:

@@ -260,8 +260,8 @@ int pn2_get_order(pn2_ctx *h, int *order, int n);
  * range[c] = {first particle, npart} */
 int pn2_get_cells(pn2_ctx *h, double *geom, int *son, int *range, double *M, double *L);
 /* interaction lists of the last step in CSR form by sink.  Call with NULL arrays to get the sizes.
- * p2p: sink leaves; src entry = source leaf cell | (image index << 26), image 0 = unshifted,
- * 1..26 = the reference's shift order (src/fmm.c:1028-1037).  m2l: sinks are cells, src = cell | image << 26. */
+ * p2p: sink leaves; src entry = source leaf cell | (image index << 27), image 0 = unshifted,
+ * 1..26 = the reference's shift order (src/fmm.c:1028-1037).  m2l: sinks are cells, src = cell | image << 27. */
 int pn2_get_lists(pn2_ctx *h, int kind /* 0 p2p, 1 m2l */, long *nseg, long *nsrc,
                   int *seg_sink, long *seg_off, int *src);
 
@@ -272,6 +272,8 @@ int pn2_fma_peak(pn2_ctx *h, int fp64, double *ops_per_s, double *ms);
 /* elapsed device time of the kernels of the last pn2_force_step*, by phase (ms): 0 tree, 1 upward,
  * 2 leaf walk + P2P (fused kernel), 3 M2L, 4 downward, 5 LET pack+exchange, 6 total, 7 frontier pass (lists by sink node) */
 int pn2_get_timings(pn2_ctx *h, double ms[8]);
+/* the same 8 values followed by: 8 the M2L kernel alone (3 also holds the sort of the pair list into CSR form) */
+int pn2_get_timings_ex(pn2_ctx *h, double *ms, int cap);
 /* CUDA-event stopwatch on the context's stream (slot 0..3): bench.py brackets its timed region with it */
 int pn2_timer_start(pn2_ctx *h, int slot);
 int pn2_timer_stop(pn2_ctx *h, int slot, double *ms);   /* records the stop event, synchronises, returns elapsed ms */

@@ -181,7 +181,7 @@ extern "C" int pn2_set_tree(pn2_ctx *h, const pn2_pack *leaf, int first_leaf, in
         pn2_set_error("pn2_set_tree: bad argument");
         return PN2_ERR_ARG;
     }
-    if ((size_t)nleaf + nnode >= (1u << PN2_IMG_SHIFT)) { pn2_set_error("pn2_set_tree: more than 2^26 cells"); return PN2_ERR_ARG; }
+    if ((size_t)nleaf + nnode >= (1u << PN2_IMG_SHIFT)) { pn2_set_error("pn2_set_tree: more than 2^27 cells"); return PN2_ERR_ARG; }
     CUDA_TRY(cudaSetDevice(h->device));
     h->nleaf = nleaf; h->nnode = nnode; h->ncell = nleaf + nnode;
     h->first_leaf = first_leaf; h->last_leaf = last_leaf; h->first_node = first_node; h->last_node = last_node;
@@ -378,6 +378,7 @@ int pn2_csr_from_device_pairs(pn2_ctx *h, int *tcell, unsigned *scell, long n, C
     h->launches += 2;
     KERNEL_CHECK();
     out->nseg = nseg;
+    out->npair = n;
     out->seg_sink = h->ic.p;
     out->seg_off = h->la.p;
     out->src = h->ub.p;

@@ -10,7 +10,7 @@
 #include "../../include/pn2gpu.h"
 
 #define NM PN2_NMULTI
-#define PN2_IMG_SHIFT 26                       // src entry = cell | image << 26
+#define PN2_IMG_SHIFT 27                       // src entry = cell | image << 27 (27 images: 5 bits; 2^27 cells per rank incl. the LET)
 #define PN2_CELL_MASK ((1u << PN2_IMG_SHIFT) - 1u)
 
 void pn2_set_error(const char *fmt, ...);
@@ -79,9 +79,10 @@ struct P2PConst {
 // CSR interaction list by sink
 struct CsrList {
     long nseg;
+    long npair = 0;           // total sources (0: unknown)
     const int *seg_sink;      // sink cell id
     const long *seg_off;      // [nseg + 1]
-    const unsigned *src;      // source cell | image << 26
+    const unsigned *src;      // source cell | image << 27
 };
 
 struct pn2_ctx {
@@ -141,7 +142,7 @@ struct pn2_ctx {
     DBuf<unsigned> spans;            // O(im) span lists of the frontier pass (16-byte units)
     unsigned long long span_cap16 = 0, span_used16 = 0, walk_visits = 0;
     DBuf<unsigned> o_head;           // [ncell]
-    DBuf<unsigned> m2l_pairs;        // [cap][2] (sink cell, src cell | image << 26), appended by the walk
+    DBuf<unsigned> m2l_pairs;        // [cap][2] (sink cell, src cell | image << 27), appended by the walk
     size_t m2l_cap = 0;
     DBuf<long> lst_off;              // dump mode: per-leaf offsets
     DBuf<unsigned> lst_src;

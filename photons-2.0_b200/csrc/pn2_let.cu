@@ -385,7 +385,7 @@ int pn2_let_unpack(pn2_ctx *h) {
     const int np = L ? L->npeer : 0;
     long rl = 0, rn = 0, rp = 0;
     for (int p = 0; p < np; p++) { rl += L->r_nl[p]; rn += L->r_nn[p]; rp += L->r_np[p]; }
-    if ((size_t)h->ncell + rl + rn >= (1u << PN2_IMG_SHIFT)) { pn2_set_error("pn2: more than 2^26 cells incl. the received LET"); return PN2_ERR_ARG; }
+    if ((size_t)h->ncell + rl + rn >= (1u << PN2_IMG_SHIFT)) { pn2_set_error("pn2: more than 2^27 cells incl. the received LET"); return PN2_ERR_ARG; }
     h->nrl = (int)rl; h->nrn = (int)rn; h->nrp = (int)rp;
     h->info.n_let_nodes = rl + rn; h->info.n_let_bodies = rp;
     std::vector<unsigned> roots;

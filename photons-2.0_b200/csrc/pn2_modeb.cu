@@ -83,7 +83,7 @@ extern "C" int pn2_step_finish(pn2_ctx *h, double *d_acc) {
     const int n = h->n;
     h->step_open = false;
     if (n == 0) {
-        for (int i = 3; i < 7; i++) CUDA_TRY(cudaEventRecord(h->ev[i], st));
+        for (int i = 3; i < 10; i++) CUDA_TRY(cudaEventRecord(h->ev[i], st));
         h->have_step = true;
         return PN2_OK;
     }
@@ -151,8 +151,9 @@ extern "C" int pn2_step_finish(pn2_ctx *h, double *d_acc) {
     if (cnt[1] > 0) {
         CsrList list;
         PN2_TRY(pn2_csr_from_device_pairs(h, (int *)h->m2l_pairs.p, h->m2l_pairs.p + h->m2l_cap, (long)cnt[1], &list));
+        CUDA_TRY(cudaEventRecord(h->ev[9], st));                       // the M2L kernel alone (after the list sort)
         PN2_TRY(pn2_launch_m2l(h, list, h->geom.p, h->M.p));
-    }
+    } else CUDA_TRY(cudaEventRecord(h->ev[9], st));
     CUDA_TRY(cudaEventRecord(h->ev[4], st));
     PN2_TRY(pn2_launch_l2l_l2p(h));
     scatter_acc_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, h->acc.p, h->order.p, d_acc);
@@ -303,5 +304,15 @@ extern "C" int pn2_get_timings(pn2_ctx *h, double ms[8]) {
     CUDA_TRY(cudaEventElapsedTime(&t, h->ev[4], h->ev[5])); ms[4] = t;     // downward
     CUDA_TRY(cudaEventElapsedTime(&t, h->ev[0], h->ev[5]));
     ms[6] = t;
+    return PN2_OK;
+}
+
+extern "C" int pn2_get_timings_ex(pn2_ctx *h, double *ms, int cap) {
+    if (!ms || cap < 8) { pn2_set_error("pn2_get_timings_ex: need room for at least 8 values"); return PN2_ERR_ARG; }
+    PN2_TRY(pn2_get_timings(h, ms));
+    for (int i = 8; i < cap; i++) ms[i] = 0.0;
+    if (h->n == 0 || cap < 9) return PN2_OK;
+    float t = 0;
+    CUDA_TRY(cudaEventElapsedTime(&t, h->ev[9], h->ev[4])); ms[8] = t;     // M2L kernel without the list sort
     return PN2_OK;
 }

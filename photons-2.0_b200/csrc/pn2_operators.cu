@@ -133,32 +133,62 @@ __global__ void __launch_bounds__(OP_WARPS * 32) l2p_kernel(int nleaf, const Lea
     }
 }
 
-// ---- M2L: one thread per sink segment, sources in list order (deterministic, no atomics) ----
-// task_compute_m2l (src/fmm.c:875-907) / task_compute_m2l_ext (src/remotes.c:598-628)
-__global__ void m2l_csr_kernel(long nseg, const int *__restrict__ seg_sink, const long *__restrict__ seg_off,
-                               const unsigned *__restrict__ src, const double *__restrict__ sink_geom,
-                               const double *__restrict__ src_geom, const double *__restrict__ src_M,
-                               double *__restrict__ L, P2PConst pc) {
-    long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= nseg) return;
-    int t = seg_sink[k];
-    double cx = sink_geom[6 * (size_t)t], cy = sink_geom[6 * (size_t)t + 1], cz = sink_geom[6 * (size_t)t + 2];
+// ---- M2L: LPS lanes per sink segment (a whole warp, or 8 lanes for short lists), sources in parallel over the lanes ----
+// task_compute_m2l (src/fmm.c:875-907) / task_compute_m2l_ext (src/remotes.c:598-628).  Every lane evaluates one
+// (sink, source) pair per round into its own 20 accumulators; the 160-byte M records of the 32 sources of a round are
+// moved by the warp through shared memory (warp_load_records: coalesced 16-byte chunks); the lanes of a sink are
+// summed with xor shuffles in a fixed order, so the result is deterministic (no atomics), and written as one
+// coalesced 160-byte record.  (The first version, one thread per sink with a serial source loop, read the M records
+// with 32 scattered sectors per load instruction and left a whole warp waiting for its longest list.)
+template <int LPS>
+__global__ void __launch_bounds__(OP_WARPS * 32) m2l_warp_kernel(long nseg, const int *__restrict__ seg_sink, const long *__restrict__ seg_off,
+                                                                 const unsigned *__restrict__ src, const double *__restrict__ sink_geom,
+                                                                 const double *__restrict__ src_geom, const double *__restrict__ src_M,
+                                                                 double *__restrict__ L, P2PConst pc) {
+    constexpr int SPW = 32 / LPS;                          // sinks per warp
+    __shared__ double s_tile[OP_WARPS][32 * REC_STRIDE];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int g = lane / LPS, gl = lane % LPS;
+    const long k = ((long)blockIdx.x * OP_WARPS + wib) * SPW + g;
+    const bool on = k < nseg;
+    int t = 0;
+    long o0 = 0, o1 = 0;
+    double cx = 0, cy = 0, cz = 0;
+    if (on) {
+        t = seg_sink[k]; o0 = seg_off[k]; o1 = seg_off[k + 1];
+        cx = sink_geom[6 * (size_t)t]; cy = sink_geom[6 * (size_t)t + 1]; cz = sink_geom[6 * (size_t)t + 2];
+    }
     double l[NM];
 #pragma unroll
     for (int i = 0; i < NM; i++) l[i] = 0.0;
-    for (long q = seg_off[k]; q < seg_off[k + 1]; q++) {
-        unsigned e = src[q];
-        unsigned s = e & PN2_CELL_MASK, img = e >> PN2_IMG_SHIFT;
+    long len = o1 - o0;
+#pragma unroll
+    for (int m = LPS; m < 32; m <<= 1) { const long other = __shfl_xor_sync(0xffffffffu, len, m); len = other > len ? other : len; }   // warp-uniform round count
+    for (long r = 0; r < len; r += LPS) {
+        const long q = o0 + r + gl;
+        const bool valid = on && q < o1;
+        unsigned e = 0;
+        if (valid) e = src[q];
+        const unsigned sc = e & PN2_CELL_MASK, img = e >> PN2_IMG_SHIFT;
         double m[NM];
-#pragma unroll
-        for (int i = 0; i < NM; i++) m[i] = src_M[(size_t)s * NM + i];
-        double sx = src_geom[6 * (size_t)s] + pc.shift[img][0];
-        double sy = src_geom[6 * (size_t)s + 1] + pc.shift[img][1];
-        double sz = src_geom[6 * (size_t)s + 2] + pc.shift[img][2];
-        m2l_add(cx - sx, cy - sy, cz - sz, m, l, pc.rs, pc.longshort);
+        warp_load_records(src_M, valid ? (int)sc : -1, m, s_tile[wib], lane);
+        if (valid) {
+            const double sx = src_geom[6 * (size_t)sc] + pc.shift[img][0];
+            const double sy = src_geom[6 * (size_t)sc + 1] + pc.shift[img][1];
+            const double sz = src_geom[6 * (size_t)sc + 2] + pc.shift[img][2];
+            m2l_add(cx - sx, cy - sy, cz - sz, m, l, pc.rs, pc.longshort);
+        }
     }
+    double mine = 0.0;                                     // lane gl < 20 of the group ends up with component gl
 #pragma unroll
-    for (int i = 0; i < NM; i++) L[(size_t)t * NM + i] += l[i];
+    for (int i = 0; i < NM; i++) {
+        double v = l[i];
+#pragma unroll
+        for (int m = 1; m < LPS; m <<= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+        if (LPS >= NM) { if (gl == i) mine = v; }
+        else if (gl == i % LPS) { if (i < LPS) mine = v; else if (on) L[(size_t)t * NM + i] += v; }
+    }
+    if (on && gl < (LPS >= NM ? NM : LPS)) L[(size_t)t * NM + gl] += mine;
 }
 
 static inline int nblk(long n, int b) { return (int)((n + b - 1) / b); }
@@ -201,8 +231,14 @@ int pn2_launch_l2l_l2p(pn2_ctx *h) {
 
 int pn2_launch_m2l(pn2_ctx *h, const CsrList &list, const double *src_geom, const double *src_M) {
     if (list.nseg == 0) return PN2_OK;
-    m2l_csr_kernel<<<nblk(list.nseg, 64), 64, 0, h->stream>>>(list.nseg, list.seg_sink, list.seg_off, list.src,
-                                                              h->geom.p, src_geom, src_M, h->L.p, h->pc);
+    // a warp per sink when the lists are long (clustered / NSIDE < particle side), 8 lanes per sink otherwise
+    const long npair = list.npair > 0 ? list.npair : 32 * list.nseg;
+    if (npair >= 24 * list.nseg)
+        m2l_warp_kernel<32><<<nblk(list.nseg, OP_WARPS), OP_WARPS * 32, 0, h->stream>>>(list.nseg, list.seg_sink, list.seg_off, list.src,
+                                                                                      h->geom.p, src_geom, src_M, h->L.p, h->pc);
+    else
+        m2l_warp_kernel<8><<<nblk(list.nseg, OP_WARPS * 4), OP_WARPS * 32, 0, h->stream>>>(list.nseg, list.seg_sink, list.seg_off, list.src,
+                                                                                         h->geom.p, src_geom, src_M, h->L.p, h->pc);
     h->launches++;
     KERNEL_CHECK();
     return PN2_OK;

@@ -305,25 +305,49 @@ __global__ void __launch_bounds__(TB) top_level_kernel(int n, const uint4 *__res
     int cur = -1;
     unsigned long long cs = 0ULL;
     unsigned cc = 0u;
+    // all loads of the thread's 4 items are issued before any is used: seg (one 16-byte load), the slot table, the payloads
+    int sv[TOP_ITEMS];
+    uint4 pv[TOP_ITEMS];
+    const bool full = base + TOP_ITEMS <= n;
+    if (full) {
+        const int4 s4 = *reinterpret_cast<const int4 *>(seg + base);
+        sv[0] = s4.x; sv[1] = s4.y; sv[2] = s4.z; sv[3] = s4.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < TOP_ITEMS; k++) sv[k] = base + k < n ? seg[base + k] : -1;
+    }
+#pragma unroll
+    for (int k = 0; k < TOP_ITEMS; k++) pv[k] = base + k < n ? pay[base + k] : make_uint4(0, 0, 0, 0);
+    if (slot2id) {
+#pragma unroll
+        for (int k = 0; k < TOP_ITEMS; k++) if (sv[k] >= 0) sv[k] = slot2id[sv[k]];       // the slot of the previous level -> node id / leaf code
+    }
+    int cv[TOP_ITEMS];
+    unsigned long long smv[TOP_ITEMS];
 #pragma unroll
     for (int k = 0; k < TOP_ITEMS; k++) {
-        const long i = base + k;
-        if (i >= n) break;
-        int s = seg[i];
-        if (s >= 0 && slot2id) s = slot2id[s];                              // the slot of the previous level -> node id / leaf code
-        if (s < 0) { seg[i] = s; continue; }                                // in a leaf: final
-        const uint4 p = pay[i];
-        const int c = n_count[s];
-        const unsigned long long sm = n_sum[s];
-        const int fl = (c < 2) ? 1 : (((unsigned long long)pay_dir(p, dir) * (unsigned long long)c > sm) ? 1 : 0);   // src/fmm.c:33-36, 60-72
+        const bool live = sv[k] >= 0 && (k == 0 || sv[k] != sv[k - 1]);                  // consecutive particles mostly share their node
+        cv[k] = live ? n_count[sv[k]] : (k > 0 ? cv[k - 1] : 0);
+        smv[k] = live ? n_sum[sv[k]] : (k > 0 ? smv[k - 1] : 0ULL);
+    }
+#pragma unroll
+    for (int k = 0; k < TOP_ITEMS; k++) {
+        const int s = sv[k];
+        if (s < 0) continue;                                                // in a leaf (or past the end): final
+        const int fl = (cv[k] < 2) ? 1 : (((unsigned long long)pay_dir(pv[k], dir) * (unsigned long long)cv[k] > smv[k]) ? 1 : 0);   // src/fmm.c:33-36, 60-72
         const int slot = 2 * (s - node0) + fl;
-        seg[i] = slot;
+        sv[k] = slot;
         if (slot != cur) {
             if (cur >= 0) table_add(cur, cs, cc);
             cur = slot; cs = 0ULL; cc = 0u;
         }
-        cs += pay_dir(p, ndir);
+        cs += pay_dir(pv[k], ndir);
         cc++;
+    }
+    if (full) *reinterpret_cast<int4 *>(seg + base) = make_int4(sv[0], sv[1], sv[2], sv[3]);
+    else {
+#pragma unroll
+        for (int k = 0; k < TOP_ITEMS; k++) if (base + k < n) seg[base + k] = sv[k];
     }
     // the thread's last run: lanes with the same slot are merged first (the common case: the whole warp)
     const unsigned peers = __match_any_sync(0xffffffffu, cur);
@@ -625,7 +649,7 @@ static int tree_build_once(pn2_ctx *h, const double *d_pos_in, int n, const pn2_
     finalize_particles_kernel<<<nb(n), TB, 0, st>>>(n, pc, d_pos_in, h->pos.p, h->order.p);
     h->launches++;
     const int nnode = node0;
-    if ((size_t)nleaf + nnode >= (1u << PN2_IMG_SHIFT)) { pn2_set_error("pn2: more than 2^26 cells on one device"); return PN2_ERR_ARG; }
+    if ((size_t)nleaf + nnode >= (1u << PN2_IMG_SHIFT)) { pn2_set_error("pn2: more than 2^27 cells on one device"); return PN2_ERR_ARG; }
     h->nleaf = nleaf; h->nnode = nnode; h->ncell = nleaf + nnode; h->nlevel = level;
     h->level_off = level_off;
     h->first_leaf = 0; h->last_leaf = nleaf; h->first_node = nleaf; h->last_node = nleaf + nnode - 1;

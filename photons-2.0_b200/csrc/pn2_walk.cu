@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NODE_MIN_BLOCKS) frontier_nod
 // finds to a per-warp queue of 16-byte entries:
 //     FP32 mode (MODE 0): {tile, dx, dy, dz}  tile = leaf tile index, d = source leaf centre - sink leaf centre
 //                                             (+ image shift) in units of lambda = 2 rs sqrt(ln 2)
-//     FP64 libm / dump modes (1, 2): {first, npart, cell | image << 26, 0}
+//     FP64 libm / dump modes (1, 2): {first, npart, cell | image << 27, 0}
 //     FP64 tile mode (MODE 3): two int4 per entry: {tile, 0, dx (double)}, {dy, dz (doubles)}, d in units of 2 rs
 template <int MODE, int QCAP>      // QCAP = queue capacity: a power of two > (entries a consumer leaves queued, < 32) + 32
 struct LeafWalk {

@@ -36,7 +36,7 @@ EXPORTS = ["pn2_create", "pn2_destroy", "pn2_set_params", "pn2_sync", "pn2_last_
            "pn2_migrate_begin", "pn2_migrate_exchange_nccl", "pn2_migrate_exchange_local", "pn2_migrate_result",
            "pn2_migrate_device", "pn2_migrate_fetch", "pn2_kick_device", "pn2_drift_device", "pn2_force_step_records",
            "pn2_pm_force_device", "pn2_pm_force_records", "pn2_pm_begin", "pn2_pm_reduce_nccl", "pn2_pm_reduce_local",
-           "pn2_pm_finish", "pn2_pm_get_mesh", "pn2_pm_get_timings", "pn2_snapshot_to_body_device", "pn2_body_to_snapshot_device"]
+           "pn2_pm_finish", "pn2_pm_get_mesh", "pn2_pm_get_timings", "pn2_snapshot_to_body_device", "pn2_body_to_snapshot_device", "pn2_get_timings_ex"]
 
 
 class Pn2Error(RuntimeError):
@@ -128,6 +128,7 @@ def lib():
     L.pn2_get_lists.argtypes = [vp, C.c_int, lp, lp, vp, vp, vp]
     L.pn2_fma_peak.argtypes = [vp, C.c_int, dp, dp]
     L.pn2_get_timings.argtypes = [vp, dp]
+    L.pn2_get_timings_ex.argtypes = [vp, dp, C.c_int]
     L.pn2_comm_unique_id.argtypes = [vp]
     L.pn2_comm_init_rank.argtypes = [vp, C.c_int, C.c_int, C.POINTER(Domain), vp]
     L.pn2_step_begin.argtypes = [vp, vp, C.c_int, C.POINTER(Domain)]
@@ -453,9 +454,9 @@ class Context:
         return sink, off, src
 
     def timings(self):
-        t = np.zeros(8)
-        _ck(lib().pn2_get_timings(self.h, t.ctypes.data_as(C.POINTER(C.c_double))))
-        return dict(zip(["tree", "upward", "walk_p2p", "m2l", "downward", "let", "total", "frontier"], t))
+        t = np.zeros(9)
+        _ck(lib().pn2_get_timings_ex(self.h, t.ctypes.data_as(C.POINTER(C.c_double)), 9))
+        return dict(zip(["tree", "upward", "walk_p2p", "m2l", "downward", "let", "total", "frontier", "m2l_kernel"], t))
 
     def fma_peak(self, fp64=False):
         ops, ms = C.c_double(), C.c_double()

@@ -60,3 +60,13 @@ def lcdm_like(nside, box=BOX, disp_rms=0.3, seed=12345, device="cpu", gamma=0.17
     # remainder can return box for tiny negative inputs
     pos = torch.where(pos >= box, pos - box, pos)
     return pos
+
+
+def poisson(n_total, box=BOX, seed=378412, device="cpu"):
+    """Uniform random (Poisson) particles: the reference's own `-2` initial condition (ic_uniform, src/initial.c:558-618:
+    ran3 with seed 378412 + rank per coordinate).  Same distribution, torch's generator instead of ran3."""
+    dev = torch.device(device)
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    pos = torch.rand((n_total, 3), generator=g, device=dev, dtype=torch.float64) * box
+    return torch.where(pos >= box, pos - box, pos)

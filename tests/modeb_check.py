@@ -2,7 +2,7 @@
 TEST INFRASTRUCTURE (uses oracle/); shared by tests/ and __graft_entry__.smoke()."""
 import numpy as np
 
-IMG = 26
+IMG = 27
 
 
 def image_shifts(box):
