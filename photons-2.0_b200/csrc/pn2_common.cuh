@@ -165,7 +165,12 @@ struct pn2_ctx {
     DBuf<double> stage_in, stage_out;   // device staging of pn2_force_step's host positions / accelerations
     std::vector<pn2_domain> all_dom;
     void *nccl = nullptr;
-    cudaEvent_t ev[10] = {nullptr};
+    cudaEvent_t ev[16] = {nullptr};
+    unsigned long long top0_host = 0;   // staging of the span bump pointer's start value
+    std::vector<unsigned> root_span_host;   // F(root) of the current walk pass
+    std::vector<int> peer_roots;            // root cell of every received LET (after pn2_let_unpack)
+    int root_count = 0;
+    bool let_unpacked = false;
     bool step_open = false;
     unsigned root_units = 0;
     cudaEvent_t tev[4][2] = {{nullptr}};
@@ -187,6 +192,8 @@ int pn2_walk_frontiers(pn2_ctx *h);
 int pn2_let_pack_all(pn2_ctx *h);
 int pn2_let_exchange_nccl(pn2_ctx *h);
 int pn2_let_unpack(pn2_ctx *h);
+int pn2_walk_set_roots(pn2_ctx *h, int which);
+int pn2_let_tree_ready(pn2_ctx *h);
 void pn2_let_release(pn2_ctx *h);
 void pn2_migrate_release(pn2_ctx *h);
 void pn2_pm_release(pn2_ctx *h);

@@ -55,6 +55,11 @@ struct LetState {
     DBuf<int> cnt_dev;                      // [2][npeer][4]
     std::vector<long> s_nl, s_nn, s_np, r_nl, r_nn, r_np;   // per peer counts
     int psize = 16;
+    // pack and exchange run on their own stream so that the walk over the local tree (pn2_modeb.cu, pass 0) hides them
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev_tree = nullptr, ev_done = nullptr;       // main stream: tree + multipoles ready; LET stream: blocks received
+    bool done_recorded = false;
+    int rank_c = -1, nranks_c = -1;
 };
 
 // same arithmetic as pruned_dev (pn2_walk.cu) / prepare_sendtree2 (src/remotes.c:97-158); this file is
@@ -203,6 +208,9 @@ void pn2_let_release(pn2_ctx *h) {
     L->reach.release(); L->lidx.release(); L->nidx.release(); L->pidx.release(); L->tbox.release();
     L->send_leaf.release(); L->send_node.release(); L->recv_leaf.release(); L->recv_node.release();
     L->send_part.release(); L->recv_part.release(); L->cnt_dev.release();
+    if (L->st) cudaStreamDestroy(L->st);
+    if (L->ev_tree) cudaEventDestroy(L->ev_tree);
+    if (L->ev_done) cudaEventDestroy(L->ev_done);
     delete L;
     h->let = nullptr;
 }
@@ -210,7 +218,13 @@ void pn2_let_release(pn2_ctx *h) {
 static LetState *let_state(pn2_ctx *h) {
     if (!h->let) h->let = new LetState();
     LetState *L = h->let;
-    if ((int)L->peers.size() != h->nranks - 1) {
+    if (!L->st) {
+        cudaStreamCreateWithFlags(&L->st, cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&L->ev_tree, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&L->ev_done, cudaEventDisableTiming);
+    }
+    if (L->rank_c != h->rank || L->nranks_c != h->nranks) {
+        L->rank_c = h->rank; L->nranks_c = h->nranks;
         L->peers.clear();
         for (int r = 0; r < h->nranks; r++) if (r != h->rank) L->peers.push_back(r);
         L->npeer = (int)L->peers.size();
@@ -218,10 +232,19 @@ static LetState *let_state(pn2_ctx *h) {
     return L;
 }
 
+// called on the main stream right after the upward pass: the point the LET stream has to wait for
+int pn2_let_tree_ready(pn2_ctx *h) {
+    LetState *L = let_state(h);
+    CUDA_TRY(cudaEventRecord(L->ev_tree, h->stream));
+    return PN2_OK;
+}
+
 // Sender side: mark, scan, pack for every peer.  Needs the tree and the multipoles (after P2M / M2M).
 int pn2_let_pack_all(pn2_ctx *h) {
     LetState *L = let_state(h);
-    cudaStream_t st = h->stream;
+    cudaStream_t st = L->st;
+    L->done_recorded = false;
+    CUDA_TRY(cudaStreamWaitEvent(st, L->ev_tree, 0));                  // tree + multipoles (pn2_let_tree_ready), not the walk enqueued behind them
     const int np = L->npeer, nleaf = h->nleaf, nnode = h->nnode, ncell = h->ncell;
     L->psize = h->prm.precision != PN2_FP32 ? 24 : 16;
     L->s_nl.assign(np, 0); L->s_nn.assign(np, 0); L->s_np.assign(np, 0);
@@ -301,11 +324,11 @@ int pn2_let_exchange_nccl(pn2_ctx *h) {
     LetState *L = let_state(h);
     const int np = L->npeer;
     L->r_nl.assign(np, 0); L->r_nn.assign(np, 0); L->r_np.assign(np, 0);
-    if (np == 0) return PN2_OK;
+    if (np == 0) { CUDA_TRY(cudaEventRecord(L->ev_done, L->st)); L->done_recorded = true; return PN2_OK; }
     if (!h->nccl) { pn2_set_error("pn2: no NCCL communicator (pn2_set_comm / pn2_comm_init_rank)"); return PN2_ERR_STATE; }
     if (!nccl_load()) return PN2_ERR_NCCL;
     ncclComm_t comm = (ncclComm_t)h->nccl;
-    cudaStream_t st = h->stream;
+    cudaStream_t st = L->st;
     PN2_TRY(L->cnt_dev.ensure(8 * (size_t)np));
     std::vector<int> sc(4 * (size_t)np), rc(4 * (size_t)np);
     for (int p = 0; p < np; p++) { sc[4 * p] = (int)L->s_nl[p]; sc[4 * p + 1] = (int)L->s_nn[p]; sc[4 * p + 2] = (int)L->s_np[p]; sc[4 * p + 3] = L->psize; }
@@ -336,6 +359,8 @@ int pn2_let_exchange_nccl(pn2_ctx *h) {
         sl += L->s_nl[p]; sn += L->s_nn[p]; sp += L->s_np[p]; rl += L->r_nl[p]; rn += L->r_nn[p]; rp += L->r_np[p];
     }
     NCCL_TRY(ncclGroupEnd());
+    CUDA_TRY(cudaEventRecord(L->ev_done, st));
+    L->done_recorded = true;
     return PN2_OK;
 }
 
@@ -345,7 +370,7 @@ extern "C" int pn2_exchange_local(pn2_ctx **hs, int nranks) {
     for (int r = 0; r < nranks; r++) {
         if (!hs[r] || hs[r]->nranks != nranks || hs[r]->rank != r) { pn2_set_error("pn2_exchange_local: context %d is not rank %d of %d", r, r, nranks); return PN2_ERR_ARG; }
         CUDA_TRY(cudaSetDevice(hs[r]->device));
-        CUDA_TRY(cudaStreamSynchronize(hs[r]->stream));
+        CUDA_TRY(cudaStreamSynchronize(let_state(hs[r])->st));          // the packs (the walk's pass 0 may still run on the main streams)
     }
     for (int r = 0; r < nranks; r++) {
         pn2_ctx *h = hs[r];
@@ -366,30 +391,35 @@ extern "C" int pn2_exchange_local(pn2_ctx **hs, int nranks) {
             LetState *S = let_state(hs[L->peers[p]]);
             long sl = 0, sn = 0, sp = 0;
             for (int k = 0; k < S->npeer && S->peers[k] != r; k++) { sl += S->s_nl[k]; sn += S->s_nn[k]; sp += S->s_np[k]; }
-            if (L->r_nl[p]) CUDA_TRY(cudaMemcpyAsync(L->recv_leaf.p + rl, S->send_leaf.p + sl, (size_t)L->r_nl[p] * sizeof(PackCell), cudaMemcpyDefault, h->stream));
-            if (L->r_nn[p]) CUDA_TRY(cudaMemcpyAsync(L->recv_node.p + rn, S->send_node.p + sn, (size_t)L->r_nn[p] * sizeof(PackCell), cudaMemcpyDefault, h->stream));
-            if (L->r_np[p]) CUDA_TRY(cudaMemcpyAsync(L->recv_part.p + (size_t)rp * L->psize, S->send_part.p + (size_t)sp * S->psize, (size_t)L->r_np[p] * L->psize, cudaMemcpyDefault, h->stream));
+            if (L->r_nl[p]) CUDA_TRY(cudaMemcpyAsync(L->recv_leaf.p + rl, S->send_leaf.p + sl, (size_t)L->r_nl[p] * sizeof(PackCell), cudaMemcpyDefault, L->st));
+            if (L->r_nn[p]) CUDA_TRY(cudaMemcpyAsync(L->recv_node.p + rn, S->send_node.p + sn, (size_t)L->r_nn[p] * sizeof(PackCell), cudaMemcpyDefault, L->st));
+            if (L->r_np[p]) CUDA_TRY(cudaMemcpyAsync(L->recv_part.p + (size_t)rp * L->psize, S->send_part.p + (size_t)sp * S->psize, (size_t)L->r_np[p] * L->psize, cudaMemcpyDefault, L->st));
             rl += L->r_nl[p]; rn += L->r_nn[p]; rp += L->r_np[p];
         }
-        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        CUDA_TRY(cudaEventRecord(L->ev_done, L->st));
+        L->done_recorded = true;
+        CUDA_TRY(cudaStreamSynchronize(L->st));
     }
     return PN2_OK;
 }
 
-// Receiver side: append the received cells / ghost particles to the unified arrays and write F(root)
+// Receiver side: append the received cells / ghost particles to the unified arrays (main stream, after the exchange
+// on the LET stream has completed)
 int pn2_let_unpack(pn2_ctx *h) {
     cudaStream_t st = h->stream;
-    const int nimg = h->prm.periodic ? 27 : 1;
     h->nrl = h->nrn = h->nrp = 0;
+    h->peer_roots.clear();
     LetState *L = h->nranks > 1 ? let_state(h) : nullptr;
     const int np = L ? L->npeer : 0;
+    if (L) {
+        if (!L->done_recorded) { pn2_set_error("pn2_step_finish: the LET blocks were not exchanged (pn2_let_exchange_nccl / pn2_exchange_local)"); return PN2_ERR_STATE; }
+        CUDA_TRY(cudaStreamWaitEvent(st, L->ev_done, 0));
+    }
     long rl = 0, rn = 0, rp = 0;
     for (int p = 0; p < np; p++) { rl += L->r_nl[p]; rn += L->r_nn[p]; rp += L->r_np[p]; }
     if ((size_t)h->ncell + rl + rn >= (1u << PN2_IMG_SHIFT)) { pn2_set_error("pn2: more than 2^27 cells incl. the received LET"); return PN2_ERR_ARG; }
     h->nrl = (int)rl; h->nrn = (int)rn; h->nrp = (int)rp;
     h->info.n_let_nodes = rl + rn; h->info.n_let_bodies = rp;
-    std::vector<unsigned> roots;
-    for (int s = 0; s < nimg; s++) roots.push_back((unsigned)h->nleaf | ((unsigned)s << PN2_IMG_SHIFT));
     if (rl + rn > 0) {
         size_t nc = (size_t)h->ncell + rl + rn;
         PN2_TRY(h->geom.ensure(6 * nc + 6, true, st)); PN2_TRY(h->son.ensure(2 * nc + 2, true, st)); PN2_TRY(h->desc.ensure(nc + 1, true, st));
@@ -405,8 +435,7 @@ int pn2_let_unpack(pn2_ctx *h) {
                                                                        h->desc.p, h->M.p);
                 h->launches++;
             }
-            if (nn > 0)       // the peer's root is its first packed node
-                for (int s = 0; s < nimg; s++) roots.push_back((unsigned)(h->ncell + (int)rl + (int)on) | ((unsigned)s << PN2_IMG_SHIFT));
+            if (nn > 0) h->peer_roots.push_back(h->ncell + (int)rl + (int)on);      // the peer's root is its first packed node
             ol += nl; on += nn; op += L->r_np[p];
         }
         if (rp > 0) {
@@ -416,18 +445,33 @@ int pn2_let_unpack(pn2_ctx *h) {
                 CUDA_TRY(cudaMemcpyAsync(h->rel.p + h->n, L->recv_part.p, (size_t)rp * 16, cudaMemcpyDeviceToDevice, st));
         }
     }
-    // F(root) as the first span: unit 1 .. ; the bump pointer starts behind it
-    size_t nroot = roots.size();
-    unsigned units = 1 + (unsigned)((nroot + 3) / 4);
-    std::vector<unsigned> span(4 * (size_t)units, 0);
+    KERNEL_CHECK();
+    return PN2_OK;
+}
+
+// F(root) of one walk pass as the first span (unit 1 ..; the bump pointer starts behind it): which = 0: the local root
+// and its periodic images (src/fmm.c:1028-1045 with the rank itself as sender); which = 1: every received root and its
+// images (src/fmm.c:1021-1027, 1039-1045).  Enqueued on the main stream; the host copy lives in the context.
+int pn2_walk_set_roots(pn2_ctx *h, int which) {
+    const int nimg = h->prm.periodic ? 27 : 1;
+    std::vector<unsigned> roots;
+    if (which == 0) {
+        if (h->nnode > 0) for (int s = 0; s < nimg; s++) roots.push_back((unsigned)h->nleaf | ((unsigned)s << PN2_IMG_SHIFT));
+    } else {
+        for (int r : h->peer_roots) for (int s = 0; s < nimg; s++) roots.push_back((unsigned)r | ((unsigned)s << PN2_IMG_SHIFT));
+    }
+    const size_t nroot = roots.size();
+    const unsigned units = 1 + (unsigned)((nroot + 3) / 4);
+    std::vector<unsigned> &span = h->root_span_host;
+    span.assign(4 * (size_t)units, 0);
     span[0] = (unsigned)nroot;
     for (size_t k = 0; k < nroot; k++) span[4 + k] = roots[k];
     if (h->span_cap16 < 1 + (unsigned long long)units) { pn2_set_error("pn2: span buffer not allocated"); return PN2_ERR_STATE; }
-    CUDA_TRY(cudaMemcpyAsync(h->spans.p + 4, span.data(), span.size() * sizeof(unsigned), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    // a pageable source: the runtime stages it before returning, so the vector may be reused by the next pass
+    CUDA_TRY(cudaMemcpyAsync(h->spans.p + 4, span.data(), span.size() * sizeof(unsigned), cudaMemcpyHostToDevice, h->stream));
     h->root_head = 1;
     h->root_units = units;
-    KERNEL_CHECK();
+    h->root_count = (int)nroot;
     return PN2_OK;
 }
 

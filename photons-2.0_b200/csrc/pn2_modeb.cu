@@ -4,6 +4,7 @@
 //   -> M2L over the pairs the walk found -> L2L + L2P -> accelerations back in caller order.
 #include <cub/cub.cuh>
 #include "pn2_common.cuh"
+#define PN2_NEV 16
 
 void pn2_modeb_release(pn2_ctx *h) {
     h->order.release(); h->parent.release(); h->depth.release(); h->b_pay.release(); h->b_pay2.release(); h->b_qc.release(); h->b_qc2.release(); h->n_sum.release(); h->b_idx2.release();
@@ -11,7 +12,7 @@ void pn2_modeb_release(pn2_ctx *h) {
     h->n_start.release(); h->n_count.release(); h->n_son.release(); h->n_depth.release(); h->l_start.release();
     h->l_count.release(); h->n_box.release(); h->n_split.release(); h->l_box.release(); h->b_cnt.release();
     h->b_scal.release(); h->stage_in.release(); h->stage_out.release(); h->m2l_pairs.release(); h->spans.release(); h->o_head.release(); h->lst_off.release(); h->lst_src.release(); h->lst_sink.release();
-    for (int i = 0; i < 10; i++) if (h->ev[i]) { cudaEventDestroy(h->ev[i]); h->ev[i] = nullptr; }
+    for (int i = 0; i < PN2_NEV; i++) if (h->ev[i]) { cudaEventDestroy(h->ev[i]); h->ev[i] = nullptr; }
     pn2_let_release(h);
     pn2_migrate_release(h);
     pn2_pm_release(h);
@@ -33,12 +34,48 @@ __global__ void iota_kernel(int n, int *o) {
 }
 
 static int ensure_events(pn2_ctx *h) {
-    for (int i = 0; i < 10; i++)
+    for (int i = 0; i < PN2_NEV; i++)
         if (!h->ev[i]) CUDA_TRY(cudaEventCreate(&h->ev[i]));
     return PN2_OK;
 }
 
-// Phase 1 of a step: tree, upward pass and (multi-rank) the LET packs for every peer
+// list-builder pools: M2L pair buffer, per-cell list heads, span buffer (96 B per particle to start with; grown on demand)
+static int ensure_walk_buffers(pn2_ctx *h) {
+    if (h->m2l_cap == 0) {
+        size_t cap = 4u << 20;
+        PN2_TRY(h->m2l_pairs.ensure(2 * cap));
+        h->m2l_cap = cap;
+    }
+    PN2_TRY(h->o_head.ensure((size_t)h->ncell + (size_t)h->nrl + (size_t)h->nrn + 1));
+    if (h->span_cap16 < 1024 + 6ULL * (unsigned long long)h->n) {
+        h->span_cap16 = 1024 + 6ULL * (unsigned long long)h->n;
+        h->spans.release();
+        PN2_TRY(h->spans.ensure(4 * (size_t)h->span_cap16));
+    }
+    return PN2_OK;
+}
+
+// One pass of the list builder + fused P2P over the sink tree for one set of source roots, enqueued on the context's
+// stream (no host synchronisation): which = 0: the local tree and its periodic images; which = 1: the received trees
+// (and their images).  The walk of a (sink, source root) pair is independent of every other root, so the two passes
+// together visit exactly the pairs of one pass over all roots; accelerations, M2L pairs and counters accumulate.
+// Pass 0 needs nothing from the peers: it runs while the LET blocks travel (pn2_let.cu).
+static int walk_pass_enqueue(pn2_ctx *h, int which, int ev_frontier, int ev_fused) {
+    cudaStream_t st = h->stream;
+    PN2_TRY(pn2_walk_set_roots(h, which));
+    if (which == 0) CUDA_TRY(cudaMemsetAsync(h->counters.p, 0, 8 * sizeof(unsigned long long), st));
+    h->top0_host = 1 + (unsigned long long)h->root_units;               // unit 0 reserved (0 = empty list), then F(root)
+    CUDA_TRY(cudaMemcpyAsync(h->counters.p + 6, &h->top0_host, sizeof h->top0_host, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(h->o_head.p, 0, ((size_t)h->ncell + 1) * sizeof(unsigned), st));
+    if (h->root_count > 0) PN2_TRY(pn2_walk_frontiers(h));
+    CUDA_TRY(cudaEventRecord(h->ev[ev_frontier], st));
+    if (h->root_count > 0) PN2_TRY(pn2_walk_fused(h, 0));
+    CUDA_TRY(cudaEventRecord(h->ev[ev_fused], st));
+    return PN2_OK;
+}
+
+// Phase 1 of a step: tree, upward pass, the walk over the local tree and its images (enqueued, not awaited) and
+// (multi-rank) the LET packs for every peer on the LET stream
 extern "C" int pn2_step_begin(pn2_ctx *h, const double *d_pos, int n, const pn2_domain *dom) {
     if (!h || n < 0 || !dom || (n > 0 && !d_pos)) { pn2_set_error("pn2_step_begin: bad argument"); return PN2_ERR_ARG; }
     for (int d = 0; d < 3; d++)
@@ -58,6 +95,7 @@ extern "C" int pn2_step_begin(pn2_ctx *h, const double *d_pos, int n, const pn2_
     cudaStream_t st = h->stream;
     h->have_step = false;
     h->step_open = false;
+    h->let_unpacked = false;
     memset(&h->info, 0, sizeof h->info);
     CUDA_TRY(cudaEventRecord(h->ev[0], st));
     PN2_TRY(pn2_tree_build_device(h, d_pos, n, dom));
@@ -69,13 +107,17 @@ extern "C" int pn2_step_begin(pn2_ctx *h, const double *d_pos, int n, const pn2_
         PN2_TRY(pn2_launch_m2m(h));
     }
     CUDA_TRY(cudaEventRecord(h->ev[2], st));
-    if (h->nranks > 1) PN2_TRY(pn2_let_pack_all(h));
-    CUDA_TRY(cudaEventRecord(h->ev[7], st));
+    if (h->nranks > 1) PN2_TRY(pn2_let_tree_ready(h));                  // what the LET stream waits for: NOT the walk enqueued next
+    if (n > 0) {
+        PN2_TRY(ensure_walk_buffers(h));
+        PN2_TRY(walk_pass_enqueue(h, 0, 10, 11));                       // local tree + images: overlaps the LET exchange
+    }
+    if (h->nranks > 1) PN2_TRY(pn2_let_pack_all(h));                    // on the LET stream, after ev[2]
     h->step_open = true;
     return PN2_OK;
 }
 
-// Phase 2 (after the LET exchange): lists + P2P, M2L, downward pass, accelerations in caller order
+// Phase 2 (after the LET exchange): the walk over the received trees, M2L, downward pass, accelerations in caller order
 extern "C" int pn2_step_finish(pn2_ctx *h, double *d_acc) {
     if (!h || !h->step_open || (h->n > 0 && !d_acc)) { pn2_set_error("pn2_step_finish: no open step / bad argument"); return PN2_ERR_ARG; }
     CUDA_TRY(cudaSetDevice(h->device));
@@ -83,34 +125,31 @@ extern "C" int pn2_step_finish(pn2_ctx *h, double *d_acc) {
     const int n = h->n;
     h->step_open = false;
     if (n == 0) {
-        for (int i = 3; i < 10; i++) CUDA_TRY(cudaEventRecord(h->ev[i], st));
+        if (h->nranks > 1) PN2_TRY(pn2_let_unpack(h));
+        for (int i = 3; i < PN2_NEV; i++) CUDA_TRY(cudaEventRecord(h->ev[i], st));
         h->have_step = true;
         return PN2_OK;
     }
-    if (h->m2l_cap == 0) {
-        size_t cap = 4u << 20;
-        PN2_TRY(h->m2l_pairs.ensure(2 * cap));
-        h->m2l_cap = cap;
-    }
-    unsigned long long cnt[8];
-    PN2_TRY(h->o_head.ensure((size_t)h->ncell + 1));
-    if (h->span_cap16 < 1024 + 6ULL * (unsigned long long)n) {
-        h->span_cap16 = 1024 + 6ULL * (unsigned long long)n;          // 96 B per particle to start with; grown on demand
-        h->spans.release();
-        PN2_TRY(h->spans.ensure(4 * (size_t)h->span_cap16));
-    }
-    PN2_TRY(pn2_let_unpack(h));                                        // also writes F(root) into the span buffer
-    CUDA_TRY(cudaEventRecord(h->ev[8], st));
+    unsigned long long cnt[8], span_used = 0;
     for (int attempt = 0;; attempt++) {
-        CUDA_TRY(cudaMemsetAsync(h->counters.p, 0, 8 * sizeof(unsigned long long), st));
-        const unsigned long long top0 = 1 + (unsigned long long)h->root_units;   // unit 0 reserved (0 = empty list), then F(root)
-        CUDA_TRY(cudaMemcpyAsync(h->counters.p + 6, &top0, sizeof top0, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemsetAsync(h->o_head.p, 0, ((size_t)h->ncell + 1) * sizeof(unsigned), st));
-        PN2_TRY(pn2_walk_frontiers(h));
-        if (attempt == 0) CUDA_TRY(cudaEventRecord(h->ev[6], st));
-        PN2_TRY(pn2_walk_fused(h, 0));
+        if (attempt > 0) {                                             // a pool was too small: both passes again
+            CUDA_TRY(cudaMemsetAsync(h->acc.p, 0, 3 * (size_t)n * sizeof(double), st));
+            PN2_TRY(walk_pass_enqueue(h, 0, 10, 11));
+        }
         CUDA_TRY(cudaMemcpyAsync(cnt, h->counters.p, sizeof cnt, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
+        span_used = cnt[6];
+        if (h->nranks > 1) {
+            if (!h->let_unpacked) { PN2_TRY(pn2_let_unpack(h)); h->let_unpacked = true; }     // waits for the exchange (LET stream)
+            CUDA_TRY(cudaEventRecord(h->ev[8], st));
+            PN2_TRY(ensure_walk_buffers(h));                           // o_head covers the received cells too
+            PN2_TRY(walk_pass_enqueue(h, 1, 12, 3));
+            CUDA_TRY(cudaMemcpyAsync(cnt, h->counters.p, sizeof cnt, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            if (cnt[6] > span_used) span_used = cnt[6];
+        } else {
+            CUDA_TRY(cudaEventRecord(h->ev[8], st)); CUDA_TRY(cudaEventRecord(h->ev[12], st)); CUDA_TRY(cudaEventRecord(h->ev[3], st));
+        }
         if (cnt[3] & 1) { pn2_set_error("pn2: walk stack overflow (pathological particle distribution)"); return PN2_ERR_NOMEM; }
         if (cnt[3] & 4) {
             pn2_set_error("pn2: a leaf is wider than 9.8 lambda = 13.6 rs: the FP32 tile layout of the long/short split cannot hold it; use PN2_FP64");
@@ -118,16 +157,15 @@ extern "C" int pn2_step_finish(pn2_ctx *h, double *d_acc) {
         }
         bool redo = false;
         if (cnt[3] & 2) {                                              // span buffer too small
-            // a pass that ran out of room truncates the deeper levels' lists, so cnt[6] can underestimate the need:
+            // a pass that ran out of room truncates the deeper levels' lists, so the counted need can be an underestimate:
             // grow at least geometrically so that the retries converge
-            unsigned long long want = cnt[6] + cnt[6] / 4 + 1024;
+            unsigned long long want = span_used + span_used / 4 + 1024;
             if (want < 2 * h->span_cap16) want = 2 * h->span_cap16;
             if (want >= (1ULL << 32)) want = (1ULL << 32) - 1;
             if (want <= h->span_cap16) { pn2_set_error("pn2: frontier lists exceed 64 GB"); return PN2_ERR_NOMEM; }
             h->span_cap16 = want;
             h->spans.release();
             PN2_TRY(h->spans.ensure(4 * (size_t)h->span_cap16));
-            PN2_TRY(pn2_let_unpack(h));                                // rewrite F(root) into the new buffer
             redo = true;
         }
         if (cnt[1] > h->m2l_cap) {                                     // M2L pair buffer too small
@@ -140,13 +178,11 @@ extern "C" int pn2_step_finish(pn2_ctx *h, double *d_acc) {
         }
         if (!redo) break;
         if (attempt >= 8) { pn2_set_error("pn2: interaction lists do not fit"); return PN2_ERR_NOMEM; }
-        CUDA_TRY(cudaMemsetAsync(h->acc.p, 0, 3 * (size_t)n * sizeof(double), st));
     }
-    h->span_used16 = cnt[6];
+    h->span_used16 = span_used;
     h->walk_visits = cnt[4];
-    h->info.n_walk_visits = (int64_t)cnt[4]; h->info.frontier_bytes = (int64_t)(16 * cnt[6]);
+    h->info.n_walk_visits = (int64_t)cnt[4]; h->info.frontier_bytes = (int64_t)(16 * span_used);
     h->info.n_interactions = (int64_t)cnt[0]; h->info.n_m2l_pairs = (int64_t)cnt[1]; h->info.n_p2p_pairs = (int64_t)cnt[2];
-    CUDA_TRY(cudaEventRecord(h->ev[3], st));
     // M2L
     if (cnt[1] > 0) {
         CsrList list;
@@ -267,6 +303,7 @@ extern "C" int pn2_get_lists(pn2_ctx *h, int kind, long *nseg, long *nsrc, int *
         return PN2_OK;
     }
     // P2P lists are never materialised by the product step: replay the walk in dump mode (count, scan, fill)
+    if (h->nranks > 1) { pn2_set_error("pn2_get_lists: the P2P list dump replays one walk pass; single-rank contexts only"); return PN2_ERR_STATE; }
     int nl = h->nleaf;
     long total = (long)h->info.n_p2p_pairs;
     *nseg = nl; *nsrc = total;
@@ -294,12 +331,16 @@ extern "C" int pn2_get_timings(pn2_ctx *h, double ms[8]) {
     for (int i = 0; i < 8; i++) ms[i] = 0.0;
     if (h->n == 0) return PN2_OK;
     CUDA_TRY(cudaEventSynchronize(h->ev[5]));
-    float t = 0;
+    float t = 0, t2 = 0;
     CUDA_TRY(cudaEventElapsedTime(&t, h->ev[0], h->ev[1])); ms[0] = t;     // tree
     CUDA_TRY(cudaEventElapsedTime(&t, h->ev[1], h->ev[2])); ms[1] = t;     // upward
-    CUDA_TRY(cudaEventElapsedTime(&t, h->ev[2], h->ev[8])); ms[5] = t;     // LET pack + exchange + unpack
-    CUDA_TRY(cudaEventElapsedTime(&t, h->ev[8], h->ev[6])); ms[7] = t;     // frontier pass (lists by sink node)
-    CUDA_TRY(cudaEventElapsedTime(&t, h->ev[6], h->ev[3])); ms[2] = t;     // fused leaf walk + P2P
+    // the walk runs in two passes: local tree + images (ev 2 -> 10 -> 11), then, once the LET blocks have arrived and are
+    // unpacked (ev 11 -> 8: what of the exchange is NOT hidden behind the first pass), the received trees (ev 8 -> 12 -> 3)
+    CUDA_TRY(cudaEventElapsedTime(&t, h->ev[11], h->ev[8])); ms[5] = t;    // LET: exposed wait + unpack
+    CUDA_TRY(cudaEventElapsedTime(&t, h->ev[2], h->ev[10])); CUDA_TRY(cudaEventElapsedTime(&t2, h->ev[8], h->ev[12]));
+    ms[7] = t + t2;                                                        // frontier passes (lists by sink node)
+    CUDA_TRY(cudaEventElapsedTime(&t, h->ev[10], h->ev[11])); CUDA_TRY(cudaEventElapsedTime(&t2, h->ev[12], h->ev[3]));
+    ms[2] = t + t2;                                                        // fused leaf walk + P2P
     CUDA_TRY(cudaEventElapsedTime(&t, h->ev[3], h->ev[4])); ms[3] = t;     // M2L
     CUDA_TRY(cudaEventElapsedTime(&t, h->ev[4], h->ev[5])); ms[4] = t;     // downward
     CUDA_TRY(cudaEventElapsedTime(&t, h->ev[0], h->ev[5]));
