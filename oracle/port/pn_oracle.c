@@ -811,19 +811,15 @@ void pno_force(const double *pos_in, int n, int P, const pno_params *prm, double
  * Same tree definition as src/fmm.c:30-264 (mean split, cycling direction, <= MAXLEAF -> leaf, boxes
  * cut by the ancestors' splits) but built level by level and in INTEGER arithmetic:
  *   q_d = trunc((x_d - lo_d) * 2^(32-e)) (uint32, 2^e > largest box extent); Morton pre-sort on the top
- *   21 bits of each q (stable); a particle goes right iff q * count > sum(q) over its node (exact 64-bit),
+ *   10 bits of each q (30-bit key, stable: ties keep the caller's order); a particle goes right iff q * count > sum(q) over its node (exact 64-bit),
  *   all of them right if count < 2 (src/fmm.c:33-36); stable partition; split = lo + (sum/count) * 2^-(32-e);
  *   breadth-first ids (per level: nodes in range order, son 0 before son 1).
  * Everything here must match the device bit for bit.
  * ------------------------------------------------------------------------------------------ */
-static unsigned long long spread21(unsigned long long v) {
-    v &= 0x1fffffULL;
-    v = (v | v << 32) & 0x1f00000000ffffULL;
-    v = (v | v << 16) & 0x1f0000ff0000ffULL;
-    v = (v | v << 8) & 0x100f00f00f00f00fULL;
-    v = (v | v << 4) & 0x10c30c30c30c30c3ULL;
-    v = (v | v << 2) & 0x1249249249249249ULL;
-    return v;
+static unsigned long long spread10(unsigned long long v) {          /* bit k of v -> bit 3k */
+    unsigned long long r = 0;
+    for (int k = 0; k < 10; k++) r |= ((v >> k) & 1ULL) << (3 * k);
+    return r;
 }
 static unsigned quant32(double x, double lo, double S) {
     double f = (x - lo) * S;
@@ -857,7 +853,7 @@ pno_tree *pno_treeB_build(const double *pos_in, int n, int maxleaf, int direct0,
     mkey *mk = (mkey *)malloc(n*sizeof(mkey));
     for (int i = 0; i < n; i++) {
         for (int d = 0; d < 3; d++) q0[3*(size_t)i+d] = quant32(pos_in[3*(size_t)i+d], bl[d], S);
-        mk[i].key = (spread21(q0[3*(size_t)i] >> 11) << 2) | (spread21(q0[3*(size_t)i+1] >> 11) << 1) | spread21(q0[3*(size_t)i+2] >> 11);
+        mk[i].key = (spread10(q0[3*(size_t)i] >> 22) << 2) | (spread10(q0[3*(size_t)i+1] >> 22) << 1) | spread10(q0[3*(size_t)i+2] >> 22);
         mk[i].idx = i;
     }
     qsort(mk, n, sizeof(mkey), mkey_cmp);

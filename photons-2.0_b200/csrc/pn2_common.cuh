@@ -149,7 +149,7 @@ struct pn2_ctx {
     DBuf<int> lst_sink;
     long lst_nsrc = 0;
     CsrList m2l_csr{};               // CSR view of the last step's M2L list (buffers ia/ic/la/ub)
-    long tree_top_target = 4096;     // deferred top levels of the tree build while n / 2^level >= this (PN2_TREE_TOP_TARGET)
+    long tree_top_target = 1024;     // deferred top levels of the tree build while n / 2^level >= this (PN2_TREE_TOP_TARGET)
     pn2_domain dom{};
     pn2_step_info info{};
     bool have_step = false;

@@ -75,6 +75,24 @@ def main():
         if rank == 0:
             print(f"NCCL NP={world} migration: {n} records of 96 bytes, every rank holds the reference's set", flush=True)
         ctx.close()
+    # ---- PM long-range force with the mesh all-reduced over NCCL (pn2_pm_force_device) against the reference's one-rank result ----
+    gp = np.load(os.path.join(ROOT, "tests", "golden", "pm_demo_ns32.npz"))
+    prm = pn2gpu.make_params(box, 32, len(pos), float(gp["mass"]), precision=pn2gpu.FP64)
+    ctx = pn2gpu.Context(prm, device=local)
+    ctx.set_comm_torch(rank, world, doms)
+    dpos = torch.from_numpy(pos[idx]).cuda()
+    dacc = torch.zeros_like(dpos)
+    for _ in range(2):
+        ctx.pm_force_device(dpos.data_ptr(), len(idx), 32, dacc.data_ptr())
+        ctx.sync()
+    ref = torch.from_numpy(gp["acc_pm"][idx]).cuda()
+    t = torch.stack([((dacc - ref) ** 2).sum(), (ref ** 2).sum()])
+    dist.all_reduce(t)
+    err = float(torch.sqrt(t[0] / t[1]))
+    if rank == 0:
+        print(f"NCCL NP={world} PM force (ncclAllReduce of the mesh): rms rel err vs the reference {err:.3e}", flush=True)
+        assert err < 1e-10, err
+    ctx.close()
     dist.destroy_process_group()
     if rank == 0:
         print("NCCL_WORKER_OK", flush=True)
