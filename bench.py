@@ -106,6 +106,31 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa(index):
+    """Run this process (and first-touch its pinned buffers) on the NUMA node the GPU hangs off: with 8 ranks copying
+    at once, remote-node pinned memory is what limits the host-pointer path (e2e).  Best effort; returns a description."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        hnd = pynvml.nvmlDeviceGetHandleByIndex(index)
+        bus = pynvml.nvmlDeviceGetPciInfo(hnd).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        node = int(open(f"/sys/bus/pci/devices/{bus[-12:].lower()}/numa_node").read())
+        if node < 0:
+            return "numa_node unknown"
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if not allowed:
+            return f"node {node}: no allowed cpus"
+        os.sched_setaffinity(0, allowed)
+        return f"node {node}, {len(allowed)} cpus"
+    except Exception as ex:
+        return "unbound (" + repr(ex)[:80] + ")"
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -258,6 +283,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa(local) if world > 1 else "not bound (one rank)"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     nside = args.nside or args.npart_side
@@ -398,7 +424,7 @@ def main():
         e_ms = float(te[0]) / args.steps
         m_chk = min(n, 1 << 22)
         e2e = {"value": n_total / (e_ms * 1e-3), "unit": "particles/s", "h2d_bytes_per_step": int(n_total) * 24,
-               "d2h_bytes_per_step": int(n_total) * 24, "ms_per_step": e_ms,
+               "d2h_bytes_per_step": int(n_total) * 24, "ms_per_step": e_ms, "host_numa_binding_rank0": numa,
                # the host-pointer call must return what the device-resident step computed (same deterministic kernels)
                "max_abs_diff_vs_device_step_rank0": float((hacc[:m_chk].to(dev) - acc[:m_chk]).abs().max()),
                "rms_acc_rank0": float(torch.sqrt((acc[:m_chk] ** 2).sum(1).mean()))}

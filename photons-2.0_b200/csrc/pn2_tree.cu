@@ -282,7 +282,7 @@ __global__ void scatter_kernel(int n, const uint4 *__restrict__ pay, const int *
 // in Morton order -- exactly the state the level-by-level partitions would have reached -- and the remaining levels
 // run as before.
 #define TOP_ITEMS 4
-#define TOP_TAB 64
+#define TOP_TAB 256
 __device__ __forceinline__ unsigned pay_dir(const uint4 &p, int dir) { return dir == 0 ? p.x : (dir == 1 ? p.y : p.z); }
 
 __global__ void __launch_bounds__(TB) top_level_kernel(int n, const uint4 *__restrict__ pay, int *__restrict__ seg,
@@ -292,10 +292,10 @@ __global__ void __launch_bounds__(TB) top_level_kernel(int n, const uint4 *__res
     __shared__ int t_key[TOP_TAB];
     __shared__ unsigned long long t_sum[TOP_TAB];
     __shared__ unsigned t_cnt[TOP_TAB];
-    if (threadIdx.x < TOP_TAB) { t_key[threadIdx.x] = -1; t_sum[threadIdx.x] = 0ULL; t_cnt[threadIdx.x] = 0u; }
+    for (int t = threadIdx.x; t < TOP_TAB; t += TB) { t_key[t] = -1; t_sum[t] = 0ULL; t_cnt[t] = 0u; }
     __syncthreads();
     auto table_add = [&](int key, unsigned long long sv, unsigned cv) {
-        unsigned hh = ((unsigned)key * 2654435761u) >> 26;                  // 6 bits
+        unsigned hh = ((unsigned)key * 2654435761u) >> 24;                  // 8 bits
         for (int probe = 0; probe < 8; probe++) {
             const int at = (int)((hh + probe) & (TOP_TAB - 1));
             const int old = atomicCAS(&t_key[at], -1, key);
@@ -358,10 +358,11 @@ __global__ void __launch_bounds__(TB) top_level_kernel(int n, const uint4 *__res
     const unsigned ct = __reduce_add_sync(peers, cc);
     if (cur >= 0 && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) table_add(cur, (unsigned long long)lo + ((unsigned long long)hi << 24), ct);
     __syncthreads();
-    if (threadIdx.x < TOP_TAB && t_key[threadIdx.x] >= 0) {
-        atomicAdd(&csum[t_key[threadIdx.x]], t_sum[threadIdx.x]);
-        atomicAdd(&ccnt[t_key[threadIdx.x]], t_cnt[threadIdx.x]);
-    }
+    for (int t = threadIdx.x; t < TOP_TAB; t += TB)
+        if (t_key[t] >= 0) {
+            atomicAdd(&csum[t_key[t]], t_sum[t]);
+            atomicAdd(&ccnt[t_key[t]], t_cnt[t]);
+        }
 }
 
 __global__ void childcount_top_kernel(int cnt, const unsigned *__restrict__ ccnt, int maxleaf, unsigned long long *__restrict__ cc) {

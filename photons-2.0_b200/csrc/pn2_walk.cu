@@ -624,6 +624,9 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, LEAF_MIN_BLOCKS) walk_fused_k
 #define F64_MIN_BLOCKS 4
 #endif
 #define F64_NST 4
+#ifndef F64_MAGIC
+#define F64_MAGIC 1
+#endif
 template <int SW>
 struct Fused64Layout {
     static constexpr int NSL = 32 / SW;
@@ -662,8 +665,16 @@ __device__ __forceinline__ void p2p_interact_tab64(const double *slot, P2PSink64
     if (LS) {
         const double u = r2 * rinv;
         const double t = fma(u, PN2_GTAB_INVH, -0.5);
+#if F64_MAGIC
+        // interval of u = round-to-nearest of u / h - 1/2, by the 2^52 + 2^51 trick: two DADD instead of an F2I and an I2F
+        // on the quarter-rate conversion pipe (shorter dependent chain in front of the table loads)
+        const double tm = t + 6755399441055744.0;
+        const int k = __double2loint(tm);
+        const double d = t - (tm - 6755399441055744.0);
+#else
         const int k = __double2int_rn(t);                     // interval of u (round-to-nearest of u / h - 1/2)
         const double d = t - (double)k;
+#endif
         const int kc = k < PN2_GTAB_K - 1 ? k : PN2_GTAB_K - 1;   // u >= 6: the zero entry
         double g = gtab[PN2_GTAB_DEG][kc];
 #pragma unroll

@@ -12,6 +12,10 @@ rep, cubin, kern = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
+for k in range(2, len(rows)):            # several captured launches: keep the first one
+    if rows[k] and rows[k][0] == "Kernel Name":
+        rows = rows[:k]
+        break
 hdr = rows[1]
 ie, iss, isrc = hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("Source")
 prof = [(r[isrc].strip(), int(r[ie]), int(r[iss])) for r in rows[2:] if len(r) > ie]
