@@ -278,9 +278,9 @@ __global__ void scatter_kernel(int n, const uint4 *__restrict__ pay, const int *
 // it and only relabel: seg[i] = child slot 2 (node - node0) + side, the children's counts and coordinate sums (of the
 // NEXT split direction: the next level needs no separate sum pass) accumulated per block in a small shared-memory
 // table and flushed with integer atomics (exact, order-independent, as in nodesum_kernel).  24 bytes of traffic per
-// particle and level instead of ~74.  One stable radix sort on the node start positions then makes the nodes contiguous
-// in Morton order -- exactly the state the level-by-level partitions would have reached -- and the remaining levels
-// run as before.
+// particle and level instead of ~74.  A stable radix sort on the node start positions makes the nodes contiguous in
+// Morton order -- exactly the state the level-by-level partitions reach -- once in the middle (so that the deep levels'
+// nodes stay block-local) and once at the end.
 #define TOP_ITEMS 4
 #define TOP_TAB 256
 __device__ __forceinline__ unsigned pay_dir(const uint4 &p, int dir) { return dir == 0 ? p.x : (dir == 1 ? p.y : p.z); }
@@ -437,7 +437,7 @@ __global__ void top_finish_kernel(int n, const int *__restrict__ seg, const int 
     int s = seg[i];
     if (s >= 0 && slot2id) s = slot2id[s];
     key[i] = (unsigned)(s >= 0 ? n_start[s] : l_start[-(s + 2)]);
-    seg_o[i] = s >= 0 ? s : -1;
+    seg_o[i] = s;                                  // node id, or the leaf code -(leaf + 2): needed again by the next sort
     iota[i] = i;
 }
 __global__ void top_gather_kernel(int n, const int *__restrict__ idx, const uint4 *__restrict__ pay, const int *__restrict__ seg, int dir,
@@ -517,7 +517,7 @@ static int tree_build_once(pn2_ctx *h, const double *d_pos_in, int n, const pn2_
     PN2_TRY(h->acc.ensure(3 * (size_t)n + 3)); PN2_TRY(h->rel.ensure((size_t)n + 1));
     PN2_TRY(h->order.ensure(n + 1)); PN2_TRY(h->b_idx2.ensure(n + 1));
     PN2_TRY(h->b_seg.ensure(n + 1)); PN2_TRY(h->b_seg2.ensure(n + 1));
-    PN2_TRY(h->b_q.ensure((size_t)(n > cap ? n : cap) + 2)); PN2_TRY(h->b_key2.ensure(n + 2)); PN2_TRY(h->b_f.ensure(n + 2)); PN2_TRY(h->b_flag.ensure((size_t)n + 16));
+    PN2_TRY(h->b_q.ensure((size_t)(n > cap ? n : cap) + 2)); PN2_TRY(h->b_key2.ensure((size_t)(n > 2 * cap ? n : 2 * cap) + 2)); PN2_TRY(h->b_f.ensure((size_t)(n > 2 * cap ? n : 2 * cap) + 2)); PN2_TRY(h->b_flag.ensure((size_t)n + 16));
     PN2_TRY(h->b_pay.ensure((size_t)n + 1)); PN2_TRY(h->b_pay2.ensure((size_t)n + 1));
     PN2_TRY(h->b_qc.ensure((size_t)n + 1)); PN2_TRY(h->b_qc2.ensure((size_t)n + 1));
     PN2_TRY(h->b_scal.ensure(16));
@@ -575,16 +575,39 @@ static int tree_build_once(pn2_ctx *h, const double *d_pos_in, int n, const pn2_
     int node0 = 0, cnt = 1, nleaf = 0, level = 0;
     std::vector<int> level_off(1, 0);
 
-    // ---- deferred top levels (see top_level_kernel): while nodes hold more than ~top_target particles on average ----
+    // ---- deferred levels (see top_level_kernel): the whole tree, with ONE intermediate sort where nodes have shrunk to
+    //      ~tree_top_target particles (afterwards a node's descendants stay inside the blocks that hold it, so the
+    //      per-block tables keep absorbing the sums down to the leaves), and the final sort into tree order.
+    //      tree_top_target > n selects the level-by-level partitions below instead (kept as the checked alternative).
     int ktop = 0;
     while (((long)n >> (ktop + 1)) >= h->tree_top_target) ktop++;
-    if (ktop > 0) {
+    const bool deferred = h->tree_top_target <= (long)n;
+    if (deferred) {
         nodesum_kernel<<<nb(((long)n + NS_ITEMS - 1) / NS_ITEMS), TB, 0, st>>>(n, qc, sg, h->n_sum.p);      // the root's sum
         h->launches++;
         unsigned long long *csum = h->b_key2.p;
         unsigned *ccnt = reinterpret_cast<unsigned *>(h->b_f.p);
         int *s2i_prev = nullptr, *s2i = h->b_idx2.p, *s2i_other = h->b_seg2.p;
-        while (cnt > 0 && level < ktop) {
+        int bits = 1;
+        while ((1L << bits) < (long)n && bits < 32) bits++;
+        // stable sort on the start position of every particle's node / leaf: contiguous nodes, Morton order inside
+        auto sort_by_start = [&]() -> int {
+            unsigned *key = h->b_qc.p, *key_s = h->b_qc2.p;
+            int *seg_m = h->b_f.p;                               // the count table is consumed
+            int *iota = s2i;                                     // the slot table that is NOT the live one
+            top_finish_kernel<<<nb(n), TB, 0, st>>>(n, sg, s2i_prev, h->n_start.p, h->l_start.p, key, seg_m, iota);
+            cub::DeviceRadixSort::SortPairs(h->tmp.p, tb5, key, key_s, iota, h->order.p, n, 0, bits, st);
+            top_gather_kernel<<<nb(n), TB, 0, st>>>(n, h->order.p, pc, seg_m, 0, po, sg, key);
+            h->launches += 3;
+            std::swap(pc, po);
+            s2i_prev = nullptr;                                  // seg holds node ids / leaf codes again
+            KERNEL_CHECK();
+            return PN2_OK;
+        };
+        bool mid_done = ktop == 0;
+        while (cnt > 0) {
+            if (level > 200) { pn2_set_error("pn2: tree deeper than 200 levels (more than MAXLEAF coincident particles?)"); return PN2_ERR_ARG; }
+            if (!mid_done && level >= ktop) { PN2_TRY(sort_by_start()); mid_done = true; }
             const int dir = (dom->direct0 + level) % 3;
             split_kernel<<<nb(cnt), TB, 0, st>>>(cnt, node0, h->n_count.p, h->n_sum.p, dom->lo[dir], invS, h->n_split.p);
             CUDA_TRY(cudaMemsetAsync(csum, 0, 2 * (size_t)cnt * sizeof(unsigned long long), st));
@@ -608,20 +631,7 @@ static int tree_build_once(pn2_ctx *h, const double *d_pos_in, int n, const pn2_
             nleaf = hs[1];
             level++;
         }
-        // one stable sort on the start positions: nodes (and finished leaves) become contiguous, Morton order inside
-        unsigned *key = h->b_qc.p, *key_s = h->b_qc2.p;
-        int *seg_m = h->b_f.p;                                   // the count table is consumed
-        int *iota = s2i;                                         // the slot table that is NOT the live one
-        top_finish_kernel<<<nb(n), TB, 0, st>>>(n, sg, s2i_prev, h->n_start.p, h->l_start.p, key, seg_m, iota);
-        int bits = 1;
-        while ((1L << bits) < (long)n && bits < 32) bits++;
-        cub::DeviceRadixSort::SortPairs(h->tmp.p, tb5, key, key_s, iota, h->order.p, n, 0, bits, st);
-        const int dirk = (dom->direct0 + level) % 3;
-        top_gather_kernel<<<nb(n), TB, 0, st>>>(n, h->order.p, pc, seg_m, dirk, po, sg, key);      // key (b_qc) is free again: the level's q
-        h->launches += 3;
-        std::swap(pc, po);
-        qc = key; qo = key_s;
-        if (cnt > 0) CUDA_TRY(cudaMemsetAsync(h->n_sum.p + node0, 0, (size_t)cnt * sizeof(unsigned long long), st));
+        PN2_TRY(sort_by_start());                                // tree order
     }
     while (cnt > 0) {
         if (level > 200) { pn2_set_error("pn2: tree deeper than 200 levels (more than MAXLEAF coincident particles?)"); return PN2_ERR_ARG; }
