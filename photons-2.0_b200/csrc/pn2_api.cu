@@ -90,7 +90,7 @@ extern "C" int pn2_destroy(pn2_ctx *h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     h->pos.release(); h->acc.release(); h->rel.release(); h->tiles.release(); h->tiles64.release(); h->gtab.release(); h->rec_pos.release(); h->rec_acc.release(); h->geom.release(); h->son.release(); h->desc.release();
-    h->M.release(); h->L.release(); h->level_nodes.release(); h->r_desc.release(); h->r_geom.release();
+    h->M.release(); h->L.release(); h->has_l.release(); h->level_nodes.release(); h->r_desc.release(); h->r_geom.release();
     h->r_M.release(); h->r_pos.release(); h->r_rel.release(); h->ia.release(); h->ib.release(); h->ic.release();
     h->id_.release(); h->la.release(); h->ua.release(); h->ub.release(); h->tmp.release(); h->counters.release();
     pn2_modeb_release(h);
@@ -242,6 +242,7 @@ extern "C" int pn2_set_tree(pn2_ctx *h, const pn2_pack *leaf, int first_leaf, in
     CUDA_TRY(cudaStreamSynchronize(h->stream));     // host vectors go out of scope
     h->have_tree = true;
     h->have_remote = false;
+    h->use_lflags = false;          // Mode A: L is cleared here and every cell carries one
     return PN2_OK;
 }
 

@@ -108,6 +108,8 @@ struct pn2_ctx {
     DBuf<int> son;             // [ncell][2]
     DBuf<LeafDesc> desc;       // [ncell] (first, npart valid for nodes too)
     DBuf<double> M, L;         // [ncell][20]
+    DBuf<unsigned char> has_l; // Mode B: [ncell] 1 = L written this step (M2L sink or below one); L itself is never cleared
+    bool use_lflags = false;
     DBuf<int> level_nodes;     // node cell ids grouped by depth
     std::vector<int> level_off;   // [nlevel + 1]
     // ---- received LET (Mode A) ----
@@ -125,7 +127,7 @@ struct pn2_ctx {
     bool have_particles = false, have_tree = false, have_remote = false;
 
     // ---- Mode B (device-built tree / lists) ----
-    DBuf<int> order;                 // [n] caller index of the k-th particle in tree order
+    DBuf<int> order, order_alt;      // [n] caller index of the k-th particle in tree order (and its double buffer)
     DBuf<int> parent, depth;         // [ncell]
     DBuf<uint4> b_pay, b_pay2;       // build payload {qx, qy, qz, caller index}, ping-pong
     DBuf<unsigned> b_qc, b_qc2;      // the current level's key
@@ -149,7 +151,7 @@ struct pn2_ctx {
     DBuf<int> lst_sink;
     long lst_nsrc = 0;
     CsrList m2l_csr{};               // CSR view of the last step's M2L list (buffers ia/ic/la/ub)
-    long tree_top_target = 1024;     // deferred top levels of the tree build while n / 2^level >= this (PN2_TREE_TOP_TARGET)
+    long tree_top_target = 1;        // PN2_TREE_TOP_TARGET > n selects the level-by-level partition builder (the checked alternative)
     pn2_domain dom{};
     pn2_step_info info{};
     bool have_step = false;

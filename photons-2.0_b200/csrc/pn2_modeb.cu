@@ -7,7 +7,7 @@
 #define PN2_NEV 16
 
 void pn2_modeb_release(pn2_ctx *h) {
-    h->order.release(); h->parent.release(); h->depth.release(); h->b_pay.release(); h->b_pay2.release(); h->b_qc.release(); h->b_qc2.release(); h->n_sum.release(); h->b_idx2.release();
+    h->order.release(); h->order_alt.release(); h->parent.release(); h->depth.release(); h->b_pay.release(); h->b_pay2.release(); h->b_qc.release(); h->b_qc2.release(); h->n_sum.release(); h->b_idx2.release();
     h->b_seg.release(); h->b_seg2.release(); h->b_q.release(); h->b_key2.release(); h->b_f.release(); h->b_flag.release();
     h->n_start.release(); h->n_count.release(); h->n_son.release(); h->n_depth.release(); h->l_start.release();
     h->l_count.release(); h->n_box.release(); h->n_split.release(); h->l_box.release(); h->b_cnt.release();
@@ -27,6 +27,11 @@ __global__ void scatter_acc_kernel(int n, const double *__restrict__ acc, const 
     out[3 * o] = acc[3 * (size_t)i];
     out[3 * o + 1] = acc[3 * (size_t)i + 1];
     out[3 * o + 2] = acc[3 * (size_t)i + 2];
+}
+// inspection only: the cells the step never gave an expansion read as zero
+__global__ void clear_unset_l_kernel(long total, const unsigned char *__restrict__ has_l, double *__restrict__ L) {
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < total && !has_l[t / NM]) L[t] = 0.0;
 }
 __global__ void iota_kernel(int n, int *o) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -267,7 +272,13 @@ extern "C" int pn2_get_cells(pn2_ctx *h, double *geom, int *son, int *range, dou
     if (geom) CUDA_TRY(cudaMemcpyAsync(geom, h->geom.p, 6 * nc * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (son) CUDA_TRY(cudaMemcpyAsync(son, h->son.p, 2 * nc * sizeof(int), cudaMemcpyDeviceToHost, st));
     if (M) CUDA_TRY(cudaMemcpyAsync(M, h->M.p, NM * nc * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (L) CUDA_TRY(cudaMemcpyAsync(L, h->L.p, NM * nc * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (L) {
+        if (h->use_lflags) {
+            clear_unset_l_kernel<<<(unsigned)((NM * nc + 255) / 256), 256, 0, st>>>((long)(NM * nc), h->has_l.p, h->L.p);
+            CUDA_TRY(cudaMemsetAsync(h->has_l.p, 1, nc, st));            // every cell holds a valid expansion now
+        }
+        CUDA_TRY(cudaMemcpyAsync(L, h->L.p, NM * nc * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
     if (range) {
         std::vector<LeafDesc> d(nc);
         CUDA_TRY(cudaMemcpyAsync(d.data(), h->desc.p, nc * sizeof(LeafDesc), cudaMemcpyDeviceToHost, st));

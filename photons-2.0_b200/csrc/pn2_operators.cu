@@ -89,18 +89,25 @@ __global__ void __launch_bounds__(OP_WARPS * 32) m2m_level_kernel(int cnt, const
 }
 
 // ---- L2L: one thread per node of one depth, pushes its L into both children ----
+// has_l (Mode B; may be NULL = every cell carries an expansion): 1 for the cells whose L has been written this step
+// (M2L sinks and everything below them).  A node without an expansion is skipped -- no loads, no stores --, a child
+// receives its first contribution as a plain store (the L array is never cleared), so the downward pass costs what the
+// M2L list makes it cost: next to nothing at NSIDE = particle side, where the walk finds a few hundred M2L pairs.
 __global__ void __launch_bounds__(OP_WARPS * 32) l2l_level_kernel(int cnt, const int *__restrict__ nodes, const int *__restrict__ son,
-                                                                  const double *__restrict__ geom, double *__restrict__ L) {
+                                                                  const double *__restrict__ geom, double *__restrict__ L,
+                                                                  unsigned char *__restrict__ has_l) {
     __shared__ double s_tile[OP_WARPS][32 * REC_STRIDE];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const bool on = k < cnt;
-    const int c = on ? nodes[k] : -1;
+    int c = on ? nodes[k] : -1;
+    if (c >= 0 && has_l && !has_l[c]) c = -1;
+    if (!__any_sync(0xffffffffu, c >= 0)) return;
     double l[NM];
     warp_load_records(L, c, l, s_tile[wib], lane);
     double cx = 0, cy = 0, cz = 0;
     int2 ch = make_int2(-1, -1);
-    if (on) {
+    if (c >= 0) {
         cx = geom[6 * (size_t)c]; cy = geom[6 * (size_t)c + 1]; cz = geom[6 * (size_t)c + 2];
         ch = *reinterpret_cast<const int2 *>(son + 2 * (size_t)c);
         if (ch.x < 0) ch.y = -1;                    // src/operator.c:524-525 returns at the first missing son
@@ -108,20 +115,24 @@ __global__ void __launch_bounds__(OP_WARPS * 32) l2l_level_kernel(int cnt, const
 #pragma unroll
     for (int s = 0; s < 2; s++) {
         const int cs = s == 0 ? ch.x : ch.y;
+        const bool had = cs >= 0 && (!has_l || has_l[cs]);
         double cl[NM];
-        warp_load_records(L, cs, cl, s_tile[wib], lane);
+        warp_load_records(L, had ? cs : -1, cl, s_tile[wib], lane);          // no expansion yet: starts from zero
         if (cs >= 0) l2l_add(geom[6 * (size_t)cs] - cx, geom[6 * (size_t)cs + 1] - cy, geom[6 * (size_t)cs + 2] - cz, l, cl);
         warp_store_records(L, cs, cl, s_tile[wib], lane);
+        if (cs >= 0 && has_l) has_l[cs] = 1;
     }
 }
 
 // ---- L2P: one thread per leaf (src/fmm.c:1056-1057 -> src/operator.c:197-251) ----
 __global__ void __launch_bounds__(OP_WARPS * 32) l2p_kernel(int nleaf, const LeafDesc *__restrict__ desc, const double *__restrict__ pos,
-                                                            const double *__restrict__ L, double *__restrict__ acc) {
+                                                            const double *__restrict__ L, double *__restrict__ acc,
+                                                            const unsigned char *__restrict__ has_l) {
     __shared__ double s_tile[OP_WARPS][32 * REC_STRIDE];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool on = k < nleaf;
+    const bool on = k < nleaf && (!has_l || has_l[k]);                   // a leaf without an expansion gets exactly 0 from L2P
+    if (!__any_sync(0xffffffffu, on)) return;
     double l[NM];
     warp_load_records(L, on ? k : -1, l, s_tile[wib], lane);
     if (!on) return;
@@ -144,7 +155,7 @@ template <int LPS>
 __global__ void __launch_bounds__(OP_WARPS * 32) m2l_warp_kernel(long nseg, const int *__restrict__ seg_sink, const long *__restrict__ seg_off,
                                                                  const unsigned *__restrict__ src, const double *__restrict__ sink_geom,
                                                                  const double *__restrict__ src_geom, const double *__restrict__ src_M,
-                                                                 double *__restrict__ L, P2PConst pc) {
+                                                                 double *__restrict__ L, P2PConst pc, unsigned char *__restrict__ has_l) {
     constexpr int SPW = 32 / LPS;                          // sinks per warp
     __shared__ double s_tile[OP_WARPS][32 * REC_STRIDE];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -154,10 +165,13 @@ __global__ void __launch_bounds__(OP_WARPS * 32) m2l_warp_kernel(long nseg, cons
     int t = 0;
     long o0 = 0, o1 = 0;
     double cx = 0, cy = 0, cz = 0;
+    bool had = true;                                       // has_l: the first contribution of the step is stored, not added
     if (on) {
         t = seg_sink[k]; o0 = seg_off[k]; o1 = seg_off[k + 1];
         cx = sink_geom[6 * (size_t)t]; cy = sink_geom[6 * (size_t)t + 1]; cz = sink_geom[6 * (size_t)t + 2];
+        if (has_l) had = has_l[t] != 0;
     }
+    __syncwarp();                                          // every lane of the sink has read its flag before one of them sets it
     double l[NM];
 #pragma unroll
     for (int i = 0; i < NM; i++) l[i] = 0.0;
@@ -186,9 +200,10 @@ __global__ void __launch_bounds__(OP_WARPS * 32) m2l_warp_kernel(long nseg, cons
 #pragma unroll
         for (int m = 1; m < LPS; m <<= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
         if (LPS >= NM) { if (gl == i) mine = v; }
-        else if (gl == i % LPS) { if (i < LPS) mine = v; else if (on) L[(size_t)t * NM + i] += v; }
+        else if (gl == i % LPS) { if (i < LPS) mine = v; else if (on) L[(size_t)t * NM + i] = had ? L[(size_t)t * NM + i] + v : v; }
     }
-    if (on && gl < (LPS >= NM ? NM : LPS)) L[(size_t)t * NM + gl] += mine;
+    if (on && gl < (LPS >= NM ? NM : LPS)) L[(size_t)t * NM + gl] = had ? L[(size_t)t * NM + gl] + mine : mine;
+    if (on && gl == 0 && has_l) has_l[t] = 1;
 }
 
 static inline int nblk(long n, int b) { return (int)((n + b - 1) / b); }
@@ -214,15 +229,16 @@ int pn2_launch_m2m(pn2_ctx *h) {
 }
 
 int pn2_launch_l2l_l2p(pn2_ctx *h) {
+    unsigned char *flags = h->use_lflags ? h->has_l.p : nullptr;
     for (int lev = 0; lev < h->nlevel; lev++) {
         int cnt = h->level_off[lev + 1] - h->level_off[lev];
         if (cnt == 0) continue;
         l2l_level_kernel<<<nblk(cnt, OP_WARPS * 32), OP_WARPS * 32, 0, h->stream>>>(cnt, h->level_nodes.p + h->level_off[lev], h->son.p,
-                                                                h->geom.p, h->L.p);
+                                                                h->geom.p, h->L.p, flags);
         h->launches++;
     }
     if (h->nleaf > 0) {
-        l2p_kernel<<<nblk(h->nleaf, OP_WARPS * 32), OP_WARPS * 32, 0, h->stream>>>(h->nleaf, h->desc.p, h->pos.p, h->L.p, h->acc.p);
+        l2p_kernel<<<nblk(h->nleaf, OP_WARPS * 32), OP_WARPS * 32, 0, h->stream>>>(h->nleaf, h->desc.p, h->pos.p, h->L.p, h->acc.p, flags);
         h->launches++;
     }
     KERNEL_CHECK();
@@ -231,14 +247,15 @@ int pn2_launch_l2l_l2p(pn2_ctx *h) {
 
 int pn2_launch_m2l(pn2_ctx *h, const CsrList &list, const double *src_geom, const double *src_M) {
     if (list.nseg == 0) return PN2_OK;
+    unsigned char *flags = h->use_lflags ? h->has_l.p : nullptr;
     // a warp per sink when the lists are long (clustered / NSIDE < particle side), 8 lanes per sink otherwise
     const long npair = list.npair > 0 ? list.npair : 32 * list.nseg;
     if (npair >= 24 * list.nseg)
         m2l_warp_kernel<32><<<nblk(list.nseg, OP_WARPS), OP_WARPS * 32, 0, h->stream>>>(list.nseg, list.seg_sink, list.seg_off, list.src,
-                                                                                      h->geom.p, src_geom, src_M, h->L.p, h->pc);
+                                                                                      h->geom.p, src_geom, src_M, h->L.p, h->pc, flags);
     else
         m2l_warp_kernel<8><<<nblk(list.nseg, OP_WARPS * 4), OP_WARPS * 32, 0, h->stream>>>(list.nseg, list.seg_sink, list.seg_off, list.src,
-                                                                                         h->geom.p, src_geom, src_M, h->L.p, h->pc);
+                                                                                         h->geom.p, src_geom, src_M, h->L.p, h->pc, flags);
     h->launches++;
     KERNEL_CHECK();
     return PN2_OK;

@@ -285,9 +285,9 @@ __global__ void scatter_kernel(int n, const uint4 *__restrict__ pay, const int *
 #define TOP_TAB 256
 __device__ __forceinline__ unsigned pay_dir(const uint4 &p, int dir) { return dir == 0 ? p.x : (dir == 1 ? p.y : p.z); }
 
-__global__ void __launch_bounds__(TB) top_level_kernel(int n, const uint4 *__restrict__ pay, int *__restrict__ seg,
-                                                       const int *__restrict__ slot2id, int node0, const int *__restrict__ n_count,
-                                                       const unsigned long long *__restrict__ n_sum, int dir, int ndir,
+__global__ void __launch_bounds__(TB) top_level_kernel(int n, const unsigned *__restrict__ qd, const unsigned *__restrict__ qn,
+                                                       int *__restrict__ seg, const int *__restrict__ slot2id, int node0,
+                                                       const int *__restrict__ n_count, const unsigned long long *__restrict__ n_sum,
                                                        unsigned long long *__restrict__ csum, unsigned *__restrict__ ccnt) {
     __shared__ int t_key[TOP_TAB];
     __shared__ unsigned long long t_sum[TOP_TAB];
@@ -307,19 +307,23 @@ __global__ void __launch_bounds__(TB) top_level_kernel(int n, const uint4 *__res
     int cur = -1;
     unsigned long long cs = 0ULL;
     unsigned cc = 0u;
-    // all loads of the thread's 4 items are issued before any is used: seg (one 16-byte load), the slot table, the payloads
+    // all loads of the thread's 4 items are issued before any is used: seg and the two coordinates (16-byte loads), the slot table
     int sv[TOP_ITEMS];
-    uint4 pv[TOP_ITEMS];
+    unsigned dv[TOP_ITEMS], nv[TOP_ITEMS];
     const bool full = base + TOP_ITEMS <= n;
     if (full) {
         const int4 s4 = *reinterpret_cast<const int4 *>(seg + base);
+        const uint4 d4 = *reinterpret_cast<const uint4 *>(qd + base), n4 = *reinterpret_cast<const uint4 *>(qn + base);
         sv[0] = s4.x; sv[1] = s4.y; sv[2] = s4.z; sv[3] = s4.w;
+        dv[0] = d4.x; dv[1] = d4.y; dv[2] = d4.z; dv[3] = d4.w;
+        nv[0] = n4.x; nv[1] = n4.y; nv[2] = n4.z; nv[3] = n4.w;
     } else {
 #pragma unroll
-        for (int k = 0; k < TOP_ITEMS; k++) sv[k] = base + k < n ? seg[base + k] : -1;
+        for (int k = 0; k < TOP_ITEMS; k++) {
+            const bool in = base + k < n;
+            sv[k] = in ? seg[base + k] : -1; dv[k] = in ? qd[base + k] : 0u; nv[k] = in ? qn[base + k] : 0u;
+        }
     }
-#pragma unroll
-    for (int k = 0; k < TOP_ITEMS; k++) pv[k] = base + k < n ? pay[base + k] : make_uint4(0, 0, 0, 0);
     if (slot2id) {
 #pragma unroll
         for (int k = 0; k < TOP_ITEMS; k++) if (sv[k] >= 0) sv[k] = slot2id[sv[k]];       // the slot of the previous level -> node id / leaf code
@@ -336,14 +340,14 @@ __global__ void __launch_bounds__(TB) top_level_kernel(int n, const uint4 *__res
     for (int k = 0; k < TOP_ITEMS; k++) {
         const int s = sv[k];
         if (s < 0) continue;                                                // in a leaf (or past the end): final
-        const int fl = (cv[k] < 2) ? 1 : (((unsigned long long)pay_dir(pv[k], dir) * (unsigned long long)cv[k] > smv[k]) ? 1 : 0);   // src/fmm.c:33-36, 60-72
+        const int fl = (cv[k] < 2) ? 1 : (((unsigned long long)dv[k] * (unsigned long long)cv[k] > smv[k]) ? 1 : 0);   // src/fmm.c:33-36, 60-72
         const int slot = 2 * (s - node0) + fl;
         sv[k] = slot;
         if (slot != cur) {
             if (cur >= 0) table_add(cur, cs, cc);
             cur = slot; cs = 0ULL; cc = 0u;
         }
-        cs += pay_dir(pv[k], ndir);
+        cs += nv[k];
         cc++;
     }
     if (full) *reinterpret_cast<int4 *>(seg + base) = make_int4(sv[0], sv[1], sv[2], sv[3]);
@@ -440,15 +444,25 @@ __global__ void top_finish_kernel(int n, const int *__restrict__ seg, const int 
     seg_o[i] = s;                                  // node id, or the leaf code -(leaf + 2): needed again by the next sort
     iota[i] = i;
 }
-__global__ void top_gather_kernel(int n, const int *__restrict__ idx, const uint4 *__restrict__ pay, const int *__restrict__ seg, int dir,
-                                  uint4 *__restrict__ pay_o, int *__restrict__ seg_o, unsigned *__restrict__ q_o) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    const int i = idx[j];
-    const uint4 p = pay[i];
-    pay_o[j] = p;
-    seg_o[j] = seg[i];
-    q_o[j] = pay_dir(p, dir);
+// Morton order -> coordinate arrays of the deferred builder (structure of arrays: a level reads two of the three)
+__global__ void gather_soa_kernel(int n, const uint4 *__restrict__ pay_in, const int *__restrict__ idx, unsigned *__restrict__ qx,
+                                  unsigned *__restrict__ qy, unsigned *__restrict__ qz, int *__restrict__ seg) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 p = pay_in[idx[i]];
+    qx[i] = p.x; qy[i] = p.y; qz[i] = p.z;
+    seg[i] = 0;                                          // everyone starts in the root
+}
+// tree order: vals[j] = Morton rank of the j-th particle in tree order, idxm[] = caller index by Morton rank
+__global__ void finalize_particles_soa_kernel(int n, const int *__restrict__ vals, const int *__restrict__ idxm,
+                                              const double *__restrict__ pos_in, double *__restrict__ pos, int *__restrict__ order) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t j = (size_t)idxm[vals[i]];
+    order[i] = (int)j;
+    pos[3 * (size_t)i] = pos_in[3 * j];
+    pos[3 * (size_t)i + 1] = pos_in[3 * j + 1];
+    pos[3 * (size_t)i + 2] = pos_in[3 * j + 2];
 }
 
 // tree-order positions and caller indices from the final payload
@@ -518,7 +532,7 @@ static int tree_build_once(pn2_ctx *h, const double *d_pos_in, int n, const pn2_
     PN2_TRY(h->order.ensure(n + 1)); PN2_TRY(h->b_idx2.ensure(n + 1));
     PN2_TRY(h->b_seg.ensure(n + 1)); PN2_TRY(h->b_seg2.ensure(n + 1));
     PN2_TRY(h->b_q.ensure((size_t)(n > cap ? n : cap) + 2)); PN2_TRY(h->b_key2.ensure((size_t)(n > 2 * cap ? n : 2 * cap) + 2)); PN2_TRY(h->b_f.ensure((size_t)(n > 2 * cap ? n : 2 * cap) + 2)); PN2_TRY(h->b_flag.ensure((size_t)n + 16));
-    PN2_TRY(h->b_pay.ensure((size_t)n + 1)); PN2_TRY(h->b_pay2.ensure((size_t)n + 1));
+    PN2_TRY(h->b_pay.ensure((size_t)n + 4)); PN2_TRY(h->b_pay2.ensure((size_t)n + 1));      // b_pay also holds the three coordinate arrays
     PN2_TRY(h->b_qc.ensure((size_t)n + 1)); PN2_TRY(h->b_qc2.ensure((size_t)n + 1));
     PN2_TRY(h->b_scal.ensure(16));
     if (n == 0) return PN2_OK;
@@ -551,7 +565,11 @@ static int tree_build_once(pn2_ctx *h, const double *d_pos_in, int n, const pn2_
     if (tb5 > need) need = tb5;
     PN2_TRY(h->tmp.ensure(need + 16));
     cub::DeviceRadixSort::SortPairs(h->tmp.p, tb, h->b_qc.p, h->b_qc2.p, h->b_idx2.p, h->order.p, n, 0, 30, st);
-    gather_pay_kernel<<<nb(n), TB, 0, st>>>(n, h->b_pay2.p, h->order.p, dom->direct0 % 3, h->b_pay.p, h->b_qc.p, h->b_seg.p);
+    const bool deferred = h->tree_top_target <= (long)n;        // PN2_TREE_TOP_TARGET > n: the level-by-level partitions instead
+    unsigned *qsoa[3] = {reinterpret_cast<unsigned *>(h->b_pay.p), reinterpret_cast<unsigned *>(h->b_pay.p) + ((size_t)n + 3) / 4 * 4,
+                         reinterpret_cast<unsigned *>(h->b_pay.p) + 2 * (((size_t)n + 3) / 4 * 4)};     // 16-byte aligned thirds of b_pay
+    if (deferred) gather_soa_kernel<<<nb(n), TB, 0, st>>>(n, h->b_pay2.p, h->order.p, qsoa[0], qsoa[1], qsoa[2], h->b_seg.p);
+    else gather_pay_kernel<<<nb(n), TB, 0, st>>>(n, h->b_pay2.p, h->order.p, dom->direct0 % 3, h->b_pay.p, h->b_qc.p, h->b_seg.p);
     h->launches += 3;
 
     // ---- root ----
@@ -575,45 +593,23 @@ static int tree_build_once(pn2_ctx *h, const double *d_pos_in, int n, const pn2_
     int node0 = 0, cnt = 1, nleaf = 0, level = 0;
     std::vector<int> level_off(1, 0);
 
-    // ---- deferred levels (see top_level_kernel): the whole tree, with ONE intermediate sort where nodes have shrunk to
-    //      ~tree_top_target particles (afterwards a node's descendants stay inside the blocks that hold it, so the
-    //      per-block tables keep absorbing the sums down to the leaves), and the final sort into tree order.
-    //      tree_top_target > n selects the level-by-level partitions below instead (kept as the checked alternative).
-    int ktop = 0;
-    while (((long)n >> (ktop + 1)) >= h->tree_top_target) ktop++;
-    const bool deferred = h->tree_top_target <= (long)n;
+    // ---- deferred levels (see top_level_kernel): every level relabels the particles where the Morton sort put them; one
+    //      stable sort on the start position of every particle's leaf then gives the tree order (Morton order inside a
+    //      leaf, as the level-by-level stable partitions give it).  The caller index is all that moves.
     if (deferred) {
-        nodesum_kernel<<<nb(((long)n + NS_ITEMS - 1) / NS_ITEMS), TB, 0, st>>>(n, qc, sg, h->n_sum.p);      // the root's sum
+        nodesum_kernel<<<nb(((long)n + NS_ITEMS - 1) / NS_ITEMS), TB, 0, st>>>(n, qsoa[dom->direct0 % 3], sg, h->n_sum.p);      // the root's sum
         h->launches++;
         unsigned long long *csum = h->b_key2.p;
         unsigned *ccnt = reinterpret_cast<unsigned *>(h->b_f.p);
         int *s2i_prev = nullptr, *s2i = h->b_idx2.p, *s2i_other = h->b_seg2.p;
-        int bits = 1;
-        while ((1L << bits) < (long)n && bits < 32) bits++;
-        // stable sort on the start position of every particle's node / leaf: contiguous nodes, Morton order inside
-        auto sort_by_start = [&]() -> int {
-            unsigned *key = h->b_qc.p, *key_s = h->b_qc2.p;
-            int *seg_m = h->b_f.p;                               // the count table is consumed
-            int *iota = s2i;                                     // the slot table that is NOT the live one
-            top_finish_kernel<<<nb(n), TB, 0, st>>>(n, sg, s2i_prev, h->n_start.p, h->l_start.p, key, seg_m, iota);
-            cub::DeviceRadixSort::SortPairs(h->tmp.p, tb5, key, key_s, iota, h->order.p, n, 0, bits, st);
-            top_gather_kernel<<<nb(n), TB, 0, st>>>(n, h->order.p, pc, seg_m, 0, po, sg, key);
-            h->launches += 3;
-            std::swap(pc, po);
-            s2i_prev = nullptr;                                  // seg holds node ids / leaf codes again
-            KERNEL_CHECK();
-            return PN2_OK;
-        };
-        bool mid_done = ktop == 0;
         while (cnt > 0) {
             if (level > 200) { pn2_set_error("pn2: tree deeper than 200 levels (more than MAXLEAF coincident particles?)"); return PN2_ERR_ARG; }
-            if (!mid_done && level >= ktop) { PN2_TRY(sort_by_start()); mid_done = true; }
             const int dir = (dom->direct0 + level) % 3;
             split_kernel<<<nb(cnt), TB, 0, st>>>(cnt, node0, h->n_count.p, h->n_sum.p, dom->lo[dir], invS, h->n_split.p);
             CUDA_TRY(cudaMemsetAsync(csum, 0, 2 * (size_t)cnt * sizeof(unsigned long long), st));
             CUDA_TRY(cudaMemsetAsync(ccnt, 0, 2 * (size_t)cnt * sizeof(unsigned), st));
-            top_level_kernel<<<nb(((long)n + TOP_ITEMS - 1) / TOP_ITEMS), TB, 0, st>>>(n, pc, sg, s2i_prev, node0, h->n_count.p, h->n_sum.p, dir,
-                                                                                   (dir + 1) % 3, csum, ccnt);
+            top_level_kernel<<<nb(((long)n + TOP_ITEMS - 1) / TOP_ITEMS), TB, 0, st>>>(n, qsoa[dir], qsoa[(dir + 1) % 3], sg, s2i_prev, node0,
+                                                                                   h->n_count.p, h->n_sum.p, csum, ccnt);
             childcount_top_kernel<<<nb(cnt + 1), TB, 0, st>>>(cnt, ccnt, maxleaf, h->b_q.p);
             cub::DeviceScan::ExclusiveSum(h->tmp.p, tb4, h->b_q.p, h->b_q.p, cnt + 1, st);
             children_top_kernel<<<nb(cnt), TB, 0, st>>>(cnt, node0, node0 + cnt, nleaf, dir, level, maxleaf, h->n_start.p, h->n_count.p,
@@ -631,7 +627,17 @@ static int tree_build_once(pn2_ctx *h, const double *d_pos_in, int n, const pn2_
             nleaf = hs[1];
             level++;
         }
-        PN2_TRY(sort_by_start());                                // tree order
+        // tree order: sort the Morton ranks by the start position of their leaf (stable), then fetch positions / caller indices
+        unsigned *key = h->b_qc.p, *key_s = h->b_qc2.p;
+        int *iota = s2i, *vals = reinterpret_cast<int *>(h->b_pay2.p);      // the caller-order payload is consumed
+        int bits = 1;
+        while ((1L << bits) < (long)n && bits < 32) bits++;
+        top_finish_kernel<<<nb(n), TB, 0, st>>>(n, sg, s2i_prev, h->n_start.p, h->l_start.p, key, reinterpret_cast<int *>(ccnt), iota);
+        cub::DeviceRadixSort::SortPairs(h->tmp.p, tb5, key, key_s, iota, vals, n, 0, bits, st);
+        PN2_TRY(h->order_alt.ensure(n + 1));
+        finalize_particles_soa_kernel<<<nb(n), TB, 0, st>>>(n, vals, h->order.p, d_pos_in, h->pos.p, h->order_alt.p);
+        h->launches += 3;
+        std::swap(h->order, h->order_alt);
     }
     while (cnt > 0) {
         if (level > 200) { pn2_set_error("pn2: tree deeper than 200 levels (more than MAXLEAF coincident particles?)"); return PN2_ERR_ARG; }
@@ -659,8 +665,10 @@ static int tree_build_once(pn2_ctx *h, const double *d_pos_in, int n, const pn2_
         nleaf = hs[1];
         level++;
     }
-    finalize_particles_kernel<<<nb(n), TB, 0, st>>>(n, pc, d_pos_in, h->pos.p, h->order.p);
-    h->launches++;
+    if (!deferred) {
+        finalize_particles_kernel<<<nb(n), TB, 0, st>>>(n, pc, d_pos_in, h->pos.p, h->order.p);
+        h->launches++;
+    }
     const int nnode = node0;
     if ((size_t)nleaf + nnode >= (1u << PN2_IMG_SHIFT)) { pn2_set_error("pn2: more than 2^27 cells on one device"); return PN2_ERR_ARG; }
     h->nleaf = nleaf; h->nnode = nnode; h->ncell = nleaf + nnode; h->nlevel = level;
@@ -674,7 +682,9 @@ static int tree_build_once(pn2_ctx *h, const double *d_pos_in, int n, const pn2_
                                                        h->n_count.p, h->n_box.p, h->n_son.p, h->n_depth.p, h->geom.p,
                                                        h->son.p, h->desc.p, h->parent.p, h->depth.p, h->level_nodes.p);
     h->launches++;
-    CUDA_TRY(cudaMemsetAsync(h->L.p, 0, NM * nc * sizeof(double), st));
+    PN2_TRY(h->has_l.ensure(nc + 1));
+    CUDA_TRY(cudaMemsetAsync(h->has_l.p, 0, nc + 1, st));                // instead of clearing 160 bytes of L per cell
+    h->use_lflags = true;
     CUDA_TRY(cudaMemsetAsync(h->acc.p, 0, 3 * (size_t)n * sizeof(double), st));
     KERNEL_CHECK();
     h->have_particles = true;
