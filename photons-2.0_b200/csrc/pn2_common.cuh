@@ -173,6 +173,7 @@ struct pn2_ctx {
     std::vector<int> peer_roots;            // root cell of every received LET (after pn2_let_unpack)
     int root_count = 0;
     bool let_unpacked = false;
+    long step_serial = 0, tiles_built_for = -1;   // the local leaf tiles are built once per step (first walk pass)
     bool step_open = false;
     unsigned root_units = 0;
     cudaEvent_t tev[4][2] = {{nullptr}};

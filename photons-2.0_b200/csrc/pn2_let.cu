@@ -157,7 +157,7 @@ __global__ void let_pack_cells_kernel(int p, int nleaf, int nnode, int ncell, co
 }
 
 __global__ void let_pack_parts_kernel(int p, int nleaf, int ncell, int maxleaf, const unsigned *__restrict__ reach,
-                                      const int *__restrict__ pidx, const LeafDesc *__restrict__ desc, const float4 *__restrict__ rel,
+                                      const int *__restrict__ pidx, const LeafDesc *__restrict__ desc, double inv_len,
                                       const double *__restrict__ pos, int fp64, unsigned char *__restrict__ out) {
     long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
     int k = (int)(t / maxleaf), j = (int)(t % maxleaf);
@@ -171,7 +171,10 @@ __global__ void let_pack_parts_kernel(int p, int nleaf, int ncell, int maxleaf, 
         const double *s = pos + 3 * (size_t)(d.first + j);
         q[0] = s[0]; q[1] = s[1]; q[2] = s[2];
     } else {
-        reinterpret_cast<float4 *>(out)[o] = rel[d.first + j];
+        // FP32 mode ships what the receiver's tiles hold: leaf-centre-relative coordinates in units of lambda (pn2_walk.cu, tile_kernel)
+        const double *s = pos + 3 * (size_t)(d.first + j);
+        reinterpret_cast<float4 *>(out)[o] = make_float4((float)((s[0] - d.c[0]) * inv_len), (float)((s[1] - d.c[1]) * inv_len),
+                                                         (float)((s[2] - d.c[2]) * inv_len), 1.f);
     }
 }
 
@@ -303,7 +306,7 @@ int pn2_let_pack_all(pn2_ctx *h) {
                                                                    h->son.p, h->desc.p, h->M.p, L->send_leaf.p + ol, L->send_node.p + on);
         long ntp = (long)nleaf * h->prm.maxleaf;
         let_pack_parts_kernel<<<(unsigned)((ntp + 255) / 256), 256, 0, st>>>(p, nleaf, ncell, h->prm.maxleaf, L->reach.p, L->pidx.p, h->desc.p,
-                                                                            h->rel.p, h->pos.p, h->prm.precision != PN2_FP32,
+                                                                            h->pc.inv_len, h->pos.p, h->prm.precision != PN2_FP32,
                                                                             L->send_part.p + (size_t)op * L->psize);
         h->launches += 2;
         ol += L->s_nl[p]; on += L->s_nn[p]; op += L->s_np[p];

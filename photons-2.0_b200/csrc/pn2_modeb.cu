@@ -101,13 +101,13 @@ extern "C" int pn2_step_begin(pn2_ctx *h, const double *d_pos, int n, const pn2_
     h->have_step = false;
     h->step_open = false;
     h->let_unpacked = false;
+    h->step_serial++;
     memset(&h->info, 0, sizeof h->info);
     CUDA_TRY(cudaEventRecord(h->ev[0], st));
     PN2_TRY(pn2_tree_build_device(h, d_pos, n, dom));
     CUDA_TRY(cudaEventRecord(h->ev[1], st));
     h->info.n = n; h->info.nleaf = h->nleaf; h->info.nnode = h->nnode; h->info.nlevel = h->nlevel;
     if (n > 0) {
-        if (h->prm.precision == PN2_FP32) PN2_TRY(pn2_launch_relpos(h, h->pos.p, h->desc.p, h->nleaf, h->rel.p, n));
         PN2_TRY(pn2_launch_p2m(h));
         PN2_TRY(pn2_launch_m2m(h));
     }

@@ -825,16 +825,21 @@ __global__ void tile64_kernel(int nt, int nleaf, int rleaf0, const LeafDesc *__r
 // particle spacing) are reported instead of being evaluated wrongly: counters[3] |= 4.
 #define PN2_PAD_SAFE 4.9f
 template <int SW>
-__global__ void tile_kernel(int nt, int nleaf, int rleaf0, const LeafDesc *__restrict__ desc, const float4 *__restrict__ rel,
-                            float *__restrict__ tiles, int longshort, unsigned long long *__restrict__ counters) {
+__global__ void tile_kernel(int nt, int nleaf, int rleaf0, int t0, const LeafDesc *__restrict__ desc, const double *__restrict__ pos,
+                            const float4 *__restrict__ rel, double inv_len, float *__restrict__ tiles, int longshort,
+                            unsigned long long *__restrict__ counters) {
     const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int tile = (int)(t / SW), j = (int)(t % SW);
+    const int tile = t0 + (int)(t / SW), j = (int)(t % SW);
     if (tile > nt) return;
     float4 p = make_float4(PN2_PAD_COORD, PN2_PAD_COORD, PN2_PAD_COORD, 0.f);
     if (tile < nt) {
         const LeafDesc d = desc[tile < nleaf ? tile : tile - nleaf + rleaf0];
         if (j < d.npart) {
-            p = rel[d.first + j];
+            if (tile < nleaf) {
+                // a local leaf: leaf-centre-relative coordinates in units of lambda, straight from the FP64 positions
+                const double *x = pos + 3 * (size_t)(d.first + j);
+                p = make_float4((float)((x[0] - d.c[0]) * inv_len), (float)((x[1] - d.c[1]) * inv_len), (float)((x[2] - d.c[2]) * inv_len), 1.f);
+            } else p = rel[d.first + j];                     // a received leaf: its sender shipped these very values
             if (longshort && fmaxf(fmaxf(fabsf(p.x), fabsf(p.y)), fabsf(p.z)) > PN2_PAD_SAFE) atomicOr(&counters[3], 4ULL);
         }
     }
@@ -918,16 +923,21 @@ int pn2_walk_fused(pn2_ctx *h, int dump) {
         a.tiles64 = h->tiles64.p; a.gtab = h->gtab.p; a.pad_tile = nt;
     }
     if (mode == 0) {
-        // leaf tiles of the local and the received leaves (+ one padding tile)
+        // leaf tiles of the local and the received leaves (+ one padding tile).  The local tiles are built once per step
+        // (the pass over the local roots); the pass over the received trees appends its tiles and a new padding tile.
         const int sw = ml <= 8 ? 8 : (ml <= 16 ? 16 : 32);
         const int nt = h->nleaf + h->nrl;
-        PN2_TRY(h->tiles.ensure(((size_t)nt + 1) * 4 * sw));
-        const long nthr = ((long)nt + 1) * sw;
+        const size_t need = ((size_t)nt + 1) * 4 * sw;
+        const bool grows = need > h->tiles.cap;                         // a new buffer: every tile again
+        PN2_TRY(h->tiles.ensure(need));
+        const int t0 = (!grows && h->tiles_built_for == h->step_serial && h->nrl > 0) ? h->nleaf : 0;
+        const long nthr = ((long)nt + 1 - t0) * sw;
         const unsigned g = (unsigned)((nthr + 255) / 256);
-        if (sw == 8) tile_kernel<8><<<g, 256, 0, h->stream>>>(nt, h->nleaf, h->ncell, h->desc.p, h->rel.p, h->tiles.p, h->prm.longshort, h->counters.p);
-        else if (sw == 16) tile_kernel<16><<<g, 256, 0, h->stream>>>(nt, h->nleaf, h->ncell, h->desc.p, h->rel.p, h->tiles.p, h->prm.longshort, h->counters.p);
-        else tile_kernel<32><<<g, 256, 0, h->stream>>>(nt, h->nleaf, h->ncell, h->desc.p, h->rel.p, h->tiles.p, h->prm.longshort, h->counters.p);
+        if (sw == 8) tile_kernel<8><<<g, 256, 0, h->stream>>>(nt, h->nleaf, h->ncell, t0, h->desc.p, h->pos.p, h->rel.p, h->pc.inv_len, h->tiles.p, h->prm.longshort, h->counters.p);
+        else if (sw == 16) tile_kernel<16><<<g, 256, 0, h->stream>>>(nt, h->nleaf, h->ncell, t0, h->desc.p, h->pos.p, h->rel.p, h->pc.inv_len, h->tiles.p, h->prm.longshort, h->counters.p);
+        else tile_kernel<32><<<g, 256, 0, h->stream>>>(nt, h->nleaf, h->ncell, t0, h->desc.p, h->pos.p, h->rel.p, h->pc.inv_len, h->tiles.p, h->prm.longshort, h->counters.p);
         h->launches++;
+        h->tiles_built_for = h->step_serial;
         a.tiles = h->tiles.p; a.pad_tile = nt;
     }
     if (ml <= 8) launch_mode<8>(h, a, mode);
