@@ -173,6 +173,9 @@ struct pn2_ctx {
     std::vector<int> peer_roots;            // root cell of every received LET (after pn2_let_unpack)
     int root_count = 0;
     bool let_unpacked = false;
+    bool walk_active = false;               // the current walk pass visits the sink tree through active lists (pass 1)
+    DBuf<int> act_nodes, act_leaf;
+    DBuf<unsigned> act_count;
     long step_serial = 0, tiles_built_for = -1;   // the local leaf tiles are built once per step (first walk pass)
     bool step_open = false;
     unsigned root_units = 0;

@@ -222,7 +222,11 @@ static LetState *let_state(pn2_ctx *h) {
     if (!h->let) h->let = new LetState();
     LetState *L = h->let;
     if (!L->st) {
-        cudaStreamCreateWithFlags(&L->st, cudaStreamNonBlocking);
+        // highest priority: its few CTAs (pack kernels, NCCL send / recv) are dispatched ahead of the walk pass that
+        // saturates the GPU on the main stream -- without it they would wait for that grid to be fully dispatched
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        cudaStreamCreateWithPriority(&L->st, cudaStreamNonBlocking, hi);
         cudaEventCreateWithFlags(&L->ev_tree, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&L->ev_done, cudaEventDisableTiming);
     }

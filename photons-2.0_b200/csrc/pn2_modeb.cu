@@ -11,7 +11,7 @@ void pn2_modeb_release(pn2_ctx *h) {
     h->b_seg.release(); h->b_seg2.release(); h->b_q.release(); h->b_key2.release(); h->b_f.release(); h->b_flag.release();
     h->n_start.release(); h->n_count.release(); h->n_son.release(); h->n_depth.release(); h->l_start.release();
     h->l_count.release(); h->n_box.release(); h->n_split.release(); h->l_box.release(); h->b_cnt.release();
-    h->b_scal.release(); h->stage_in.release(); h->stage_out.release(); h->m2l_pairs.release(); h->spans.release(); h->o_head.release(); h->lst_off.release(); h->lst_src.release(); h->lst_sink.release();
+    h->b_scal.release(); h->act_nodes.release(); h->act_leaf.release(); h->act_count.release(); h->stage_in.release(); h->stage_out.release(); h->m2l_pairs.release(); h->spans.release(); h->o_head.release(); h->lst_off.release(); h->lst_src.release(); h->lst_sink.release();
     for (int i = 0; i < PN2_NEV; i++) if (h->ev[i]) { cudaEventDestroy(h->ev[i]); h->ev[i] = nullptr; }
     pn2_let_release(h);
     pn2_migrate_release(h);
@@ -67,6 +67,7 @@ static int ensure_walk_buffers(pn2_ctx *h) {
 // Pass 0 needs nothing from the peers: it runs while the LET blocks travel (pn2_let.cu).
 static int walk_pass_enqueue(pn2_ctx *h, int which, int ev_frontier, int ev_fused) {
     cudaStream_t st = h->stream;
+    h->walk_active = which == 1;
     PN2_TRY(pn2_walk_set_roots(h, which));
     if (which == 0) CUDA_TRY(cudaMemsetAsync(h->counters.p, 0, 8 * sizeof(unsigned long long), st));
     h->top0_host = 1 + (unsigned long long)h->root_units;               // unit 0 reserved (0 = empty list), then F(root)
@@ -184,6 +185,7 @@ extern "C" int pn2_step_finish(pn2_ctx *h, double *d_acc) {
         if (!redo) break;
         if (attempt >= 8) { pn2_set_error("pn2: interaction lists do not fit"); return PN2_ERR_NOMEM; }
     }
+    h->walk_active = false;
     h->span_used16 = span_used;
     h->walk_visits = cnt[4];
     h->info.n_walk_visits = (int64_t)cnt[4]; h->info.frontier_bytes = (int64_t)(16 * span_used);

@@ -62,6 +62,14 @@ struct WalkArgs {
     int pass, emit_m2l;
     const int *work;                   // node kernel: cells of this level
     int nwork;
+    // pass over the received trees: only the part of the sink tree that such a source can reach is visited.  A node that
+    // hands a non-empty O(im) to its sons appends them to the next level's active list / the active leaf list; a level's
+    // (or the leaf kernel's) launch covers the worst case and CTAs beyond the device-side count exit at once.
+    const unsigned *work_count;        // != NULL: work[] holds *work_count entries (device counter)
+    int *next_work;                    // node kernel: active list of the next level (or NULL)
+    unsigned *next_count;
+    int *leaf_work;                    // node kernel: active sink leaves (or NULL)
+    unsigned *leaf_count;
 };
 
 // acceptance(), src/fmm.c:267-326: 0 open, 1 accept, -1 drop.  Same expressions in the same order (this file is
@@ -167,7 +175,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NODE_MIN_BLOCKS) frontier_nod
     __shared__ unsigned s_obuf[WALK_WARPS][OBUF_CAP];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int wk = blockIdx.x * WALK_WARPS + wib;
-    if (wk >= a.nwork) return;
+    if (wk >= a.nwork || (a.work_count && (unsigned)wk >= *a.work_count)) return;
     const int im = a.work[wk];
     const unsigned lt_mask = (1u << lane) - 1u;
     unsigned *stack = s_stack[wib], *obuf = s_obuf[wib];
@@ -282,6 +290,16 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NODE_MIN_BLOCKS) frontier_nod
         a.o_head[im] = first_span;
         if (err) atomicOr(&a.counters[3], (unsigned long long)err);
         atomicAdd(&a.counters[4], visits);
+        if (a.next_work && first_span) {                   // the sons inherit a non-empty frontier: they are active
+            const int2 ch = *reinterpret_cast<const int2 *>(a.son + 2 * (size_t)im);
+            const int sv[2] = {ch.x, ch.y};
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                if (sv[q] < 0) continue;
+                if (sv[q] < a.nleaf) a.leaf_work[atomicAdd(a.leaf_count, 1u)] = sv[q];
+                else a.next_work[atomicAdd(a.next_count, 1u)] = sv[q];
+            }
+        }
     }
 }
 
@@ -416,8 +434,12 @@ __global__ void __launch_bounds__(WALK_WARPS * 32) walk_leaf_kernel(WalkArgs a, 
     __shared__ int4 s_srcq[WALK_WARPS][SRCQ_CAP];
     __shared__ double s_sink[WALK_WARPS][6];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int leaf = blockIdx.x * WALK_WARPS + wib;
+    int leaf = blockIdx.x * WALK_WARPS + wib;
     if (leaf >= a.nleaf) return;
+    if (a.work_count) {
+        if ((unsigned)leaf >= *a.work_count) return;
+        leaf = a.work[leaf];
+    }
     const int q = lane / SW, j = lane % SW;
     LeafWalk<MODE, SRCQ_CAP> w;
     w.begin(a, leaf, s_stack[wib], s_srcq[wib], s_sink[wib], lane);
@@ -514,8 +536,12 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, LEAF_MIN_BLOCKS) walk_fused_k
     __shared__ __align__(16) unsigned char s_stage[WALK_WARPS][FL::STAGE_BYTES];
     __shared__ double s_sink[WALK_WARPS][6];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int leaf = blockIdx.x * WALK_WARPS + wib;
+    int leaf = blockIdx.x * WALK_WARPS + wib;
     if (leaf >= a.nleaf) return;
+    if (a.work_count) {                                    // pass over the received trees: active leaves only
+        if ((unsigned)leaf >= *a.work_count) return;
+        leaf = a.work[leaf];
+    }
     const int q = lane / SW, j = lane % SW;
     LeafWalk<0, SRCQ_CAP> w;
     w.begin(a, leaf, s_stack[wib], s_srcq[wib], s_sink[wib], lane);
@@ -700,8 +726,12 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, F64_MIN_BLOCKS) walk_fused_f6
     for (int i = threadIdx.x; i < (PN2_GTAB_DEG + 1) * PN2_GTAB_K; i += blockDim.x) (&s_gtab[0][0])[i] = a.gtab[i];
     __syncthreads();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int leaf = blockIdx.x * WALK_WARPS + wib;
+    int leaf = blockIdx.x * WALK_WARPS + wib;
     if (leaf >= a.nleaf) return;
+    if (a.work_count) {
+        if ((unsigned)leaf >= *a.work_count) return;
+        leaf = a.work[leaf];
+    }
     const int q = lane / SW, j = lane % SW;
     LeafWalk<3, SRCQ_CAP> w;
     w.begin(a, leaf, s_stack[wib], s_srcq[wib], s_sink[wib], lane);
@@ -878,15 +908,35 @@ static void fill_args(pn2_ctx *h, WalkArgs &a) {
 }
 
 // Pass 1 over all levels.  counters[6] is the span bump pointer (unit 0 is reserved: 0 = "no span").
+// h->walk_active: the pass over the received trees -- levels and leaves are visited through active lists built on the way.
 int pn2_walk_frontiers(pn2_ctx *h) {
     if (h->nnode == 0) return PN2_OK;
     WalkArgs a;
     fill_args(h, a);
     a.emit_m2l = 1;
+    if (h->walk_active) {
+        // act_nodes: one region per level (the level's nodes at most); act_leaf: nleaf; act_count: [nlevel + 1] counters, the last for the leaves
+        PN2_TRY(h->act_nodes.ensure((size_t)h->nnode + 1)); PN2_TRY(h->act_leaf.ensure((size_t)h->nleaf + 1));
+        PN2_TRY(h->act_count.ensure((size_t)h->nlevel + 2));
+        CUDA_TRY(cudaMemsetAsync(h->act_count.p, 0, ((size_t)h->nlevel + 2) * sizeof(unsigned), h->stream));
+        const int root = h->nleaf;
+        const unsigned one = 1u;
+        CUDA_TRY(cudaMemcpyAsync(h->act_nodes.p, &root, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(cudaMemcpyAsync(h->act_count.p, &one, sizeof(unsigned), cudaMemcpyHostToDevice, h->stream));
+    }
     for (int lev = 0; lev < h->nlevel; lev++) {
         int cnt = h->level_off[lev + 1] - h->level_off[lev];
         if (cnt == 0) continue;
-        a.work = h->level_nodes.p + h->level_off[lev];
+        if (h->walk_active) {
+            a.work = h->act_nodes.p + h->level_off[lev];
+            a.work_count = h->act_count.p + lev;
+            a.next_work = lev + 1 < h->nlevel ? h->act_nodes.p + h->level_off[lev + 1] : h->act_nodes.p;     // the last level has no node sons
+            a.next_count = h->act_count.p + lev + 1;
+            a.leaf_work = h->act_leaf.p;
+            a.leaf_count = h->act_count.p + h->nlevel + 1;
+        } else {
+            a.work = h->level_nodes.p + h->level_off[lev];
+        }
         a.nwork = cnt;
         frontier_node_kernel<<<(cnt + WALK_WARPS - 1) / WALK_WARPS, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
         h->launches++;
@@ -903,6 +953,7 @@ int pn2_walk_fused(pn2_ctx *h, int dump) {
     fill_args(h, a);
     a.pass = dump == 2 ? 1 : 0;
     a.emit_m2l = dump == 0;
+    if (h->walk_active && dump == 0) { a.work = h->act_leaf.p; a.work_count = h->act_count.p + h->nlevel + 1; }
     // PN2_FP64: table-driven FP64 kernel (3); PN2_FP64_LIBM: the reference's expression with libm (1); PN2_FP32: 0
     int mode = dump ? 2 : (h->prm.precision == PN2_FP64 ? 3 : (h->prm.precision == PN2_FP64_LIBM ? 1 : 0));
     int ml = h->prm.maxleaf;
