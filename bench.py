@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--cpu-sample-side", type=int, default=96, help="particles per dimension of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--pm", action="store_true", help="also time the PM long-range force (pn2_pm_force_device, NSIDE mesh) on the same particles")
     ap.add_argument("--rebalance", type=int, default=0,
                     help="after the timed region (N > 1): this many iterations of the reference's load-balance loop -- DTIME_FRACTION from the "
                          "ranks' list sizes, determine_split_domtree, particle migration, force step -- reported as `rebalance`")
@@ -429,6 +430,28 @@ def main():
                "max_abs_diff_vs_device_step_rank0": float((hacc[:m_chk].to(dev) - acc[:m_chk]).abs().max()),
                "rms_acc_rank0": float(torch.sqrt((acc[:m_chk] ** 2).sum(1).mean()))}
 
+    # ---- PM long-range force on the same particles (not part of the metric) ----
+    pm = None
+    if args.pm and args.ic != "merger":
+        apm = torch.empty_like(pos)
+        for _ in range(2):
+            ctx.pm_force_device(pos.data_ptr(), n, nside, apm.data_ptr())
+        barrier()
+        ctx.timer_start(2)
+        for _ in range(3):
+            ctx.pm_force_device(pos.data_ptr(), n, nside, apm.data_ptr())
+        pm_ms = ctx.timer_stop(2) / 3
+        ph = ctx.pm_timings()
+        tp = torch.tensor([pm_ms], dtype=torch.float64, device=dev)
+        mp = torch.cat([apm.sum(0), torch.linalg.vector_norm(apm, dim=1).sum().reshape(1)])
+        if world > 1:
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+            dist.all_reduce(mp, op=dist.ReduceOp.SUM)
+        pm = {"ms": float(tp[0]), "nside": nside, "mesh_bytes": 8 * nside ** 3, "phases_ms_rank0": {k: float(v) for k, v in ph.items()},
+              "momentum_residual": float(torch.linalg.vector_norm(mp[:3]) / mp[3]),
+              "what": "CIC deposit + ncclAllReduce of the mesh + cuFFT D2Z / Green function / Z2D + 4-point gradient and CIC gather, particles in caller order"}
+        del apm
+
     # ---- the reference's load-balance loop (src/photoNs.c:270-283, src/domains.c:21-160, 268-375) on the measured load ----
     rebalance = None
     if args.rebalance > 0 and world > 1:
@@ -492,7 +515,7 @@ def main():
            "config": workload_config(args, world),
            "p2p_ginteractions_per_s": nint_total / (ms_step * 1e-3) / 1e9,
            "interactions_per_particle": nint_total / n_total,
-           "migrate": migrate, "momentum_residual": momentum_residual, "rebalance": rebalance,
+           "migrate": migrate, "momentum_residual": momentum_residual, "rebalance": rebalance, "pm_long_range": pm,
            "phases_ms": {k: float(np.mean([p[k] for p in phase])) for k in ("tree", "upward", "frontier", "walk_p2p", "m2l", "m2l_kernel", "downward", "let", "total")},
            "tree": {"nleaf": info["nleaf"], "nnode": info["nnode"], "levels": info["nlevel"], "m2l_pairs": info["n_m2l_pairs"],
                     "p2p_leaf_pairs": info["n_p2p_pairs"], "walk_visits": info["n_walk_visits"],
