@@ -79,7 +79,6 @@ extern "C" int pn2_create(pn2_ctx **out, int device, const pn2_params *prm) {
     CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     pn2_init_consts(h);
     if (const char *e = getenv("PN2_TREE_TOP_TARGET")) { long v = atol(e); if (v >= 1) h->tree_top_target = v; }
-    if (const char *e = getenv("PN2_RAGGED")) h->ragged_mode = atoi(e) ? 1 : 0;
     PN2_TRY(h->counters.ensure(8));
     CUDA_TRY(cudaMemsetAsync(h->counters.p, 0, 8 * sizeof(unsigned long long), h->stream));
     *out = h;

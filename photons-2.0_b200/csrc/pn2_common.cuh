@@ -173,7 +173,6 @@ struct pn2_ctx {
     std::vector<int> peer_roots;            // root cell of every received LET (after pn2_let_unpack)
     int root_count = 0;
     bool let_unpacked = false;
-    int ragged_mode = -1;                   // FP32 fused kernel for sparsely filled leaves: -1 by mean occupancy, 0 never, 1 always (PN2_RAGGED)
     bool walk_active = false;               // the current walk pass visits the sink tree through active lists (pass 1)
     DBuf<int> act_nodes, act_leaf;
     DBuf<unsigned> act_count;

@@ -312,7 +312,6 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NODE_MIN_BLOCKS) frontier_nod
 //                                             (+ image shift) in units of lambda = 2 rs sqrt(ln 2)
 //     FP64 libm / dump modes (1, 2): {first, npart, cell | image << 27, 0}
 //     FP64 tile mode (MODE 3): two int4 per entry: {tile, 0, dx (double)}, {dy, dz (doubles)}, d in units of 2 rs
-//     FP32 ragged mode (MODE 4): as MODE 0 with (occupied source pairs - 1) in bits 27..30 of the tile word
 template <int MODE, int QCAP>      // QCAP = queue capacity: a power of two > (entries a consumer leaves queued, < 32) + 32
 struct LeafWalk {
     SpanReader rd;
@@ -375,9 +374,8 @@ struct LeafWalk {
                 // leaf x leaf: always a P2P pair (src/fmm.c:438-451, src/remotes.c:228-240)
                 emit_p = 1;
                 const int dfirst = __double2loint(r1.y), dnpart = __double2hiint(r1.y);
-                if (MODE == 0 || MODE == 4) {
+                if (MODE == 0) {
                     ent.x = jm < a.nleaf ? jm : jm - a.rleaf0 + a.nleaf;
-                    if (MODE == 4) ent.x |= (((dnpart > 0 ? dnpart : 1) + 1) / 2 - 1) << 27;
                     ent.y = __float_as_int((float)(((r0.x + pc.shift[img][0]) - sd.c[0]) * pc.inv_len));
                     ent.z = __float_as_int((float)(((r0.y + pc.shift[img][1]) - sd.c[1]) * pc.inv_len));
                     ent.w = __float_as_int((float)(((r1.x + pc.shift[img][2]) - sd.c[2]) * pc.inv_len));
@@ -529,18 +527,15 @@ __device__ __forceinline__ void cp_async16(unsigned dst_shared, const void *src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// RG ("ragged"): for sparsely filled leaves (Poisson / clustered sets: 5.9 of 8 slots on average) the batch's source
-// leaves are ordered by their number of occupied slot pairs (a counting sort over the warp: SW/2 ballots) and a stage
-// only runs the pairs its fullest leaf has -- the skipped pairs are padding whose contribution is exactly 0.  The
-// headline workload (7.94 of 8 slots) keeps the straight-line kernel.
-#define PN2_TILE_MASK 0x07ffffff
-template <int SW, bool LS, bool RG = false>      // LS: with the long/short split factor g(r / 2rs)
+// (A "ragged" variant for sparsely filled leaves -- batch ordered by occupied slot pairs, a stage running only the pairs
+// its fullest source leaf has -- was built and measured slower: the per-stage trip count breaks the straight-line 8-stage
+// block the scheduler interleaves; Poisson 256^3 83.8 vs 76.6 ms, profiles/r02n_sweep_ragged.log.  Removed.)
+template <int SW, bool LS>      // LS: with the long/short split factor g(r / 2rs)
 __global__ void __launch_bounds__(WALK_WARPS * 32, LEAF_MIN_BLOCKS) walk_fused_kernel(WalkArgs a, P2PConst pc) {
     using FL = FusedLayout<SW>;
     constexpr int NSL = FL::NSL, NST = FL::NST, BATCH = FL::BATCH, TB = FL::TB, ROWB = FL::ROWB;
     __shared__ unsigned s_stack[WALK_WARPS][STACK_CAP];
     __shared__ int4 s_srcq[WALK_WARPS][SRCQ_CAP];
-    __shared__ int4 s_sorted[RG ? WALK_WARPS : 1][RG ? 32 : 1];
     __shared__ __align__(16) unsigned char s_stage[WALK_WARPS][FL::STAGE_BYTES];
     __shared__ double s_sink[WALK_WARPS][6];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -551,7 +546,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, LEAF_MIN_BLOCKS) walk_fused_k
         leaf = a.work[leaf];
     }
     const int q = lane / SW, j = lane % SW;
-    LeafWalk<RG ? 4 : 0, SRCQ_CAP> w;
+    LeafWalk<0, SRCQ_CAP> w;
     w.begin(a, leaf, s_stack[wib], s_srcq[wib], s_sink[wib], lane);
     // sink: slot j of the leaf's own tile (padding slots compute, but are never written)
     float xi, yi, zi;
@@ -568,26 +563,11 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, LEAF_MIN_BLOCKS) walk_fused_k
     const unsigned stage_dst = (unsigned)__cvta_generic_to_shared(stage) + q * ROWB + j * 16;   // this lane's 16-byte chunk of row q
     const char *tile_src = reinterpret_cast<const char *>(a.tiles) + j * 16;
     auto issue_batch = [&](int cnt) {      // cnt <= BATCH queue entries from qhead, a multiple of NSL
-        if (RG) {
-            // fullest source leaves first: counting sort of the batch on the pair count (stable)
-            int4 mine = make_int4(0, 0, 0, 0);
-            int key = -1;
-            if (lane < cnt) { mine = w.queue[(qhead + lane) & (SRCQ_CAP - 1)]; key = (mine.x >> 27) & 15; }
-            int at = 0, base = 0;
-#pragma unroll
-            for (int k = SW / 2 - 1; k >= 0; k--) {
-                const unsigned m = __ballot_sync(0xffffffffu, key == k);
-                if (key == k) at = base + __popc(m & ((1u << lane) - 1u));
-                base += __popc(m);
-            }
-            if (lane < cnt) s_sorted[wib][at] = mine;
-            __syncwarp();
-        }
 #pragma unroll
         for (int s = 0; s < NST; s++) {
             if (s * NSL < cnt) {
-                const int4 e = RG ? s_sorted[wib][s * NSL + q] : w.queue[(qhead + s * NSL + q) & (SRCQ_CAP - 1)];
-                cp_async16(stage_dst + s * NSL * ROWB, tile_src + (size_t)(RG ? (e.x & PN2_TILE_MASK) : e.x) * TB);
+                const int4 e = w.queue[(qhead + s * NSL + q) & (SRCQ_CAP - 1)];
+                cp_async16(stage_dst + s * NSL * ROWB, tile_src + (size_t)e.x * TB);
                 if (j == 0) *reinterpret_cast<int4 *>(stage + (s * NSL + q) * ROWB + TB) = e;
             }
         }
@@ -600,13 +580,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, LEAF_MIN_BLOCKS) walk_fused_k
         const float4 o = *reinterpret_cast<const float4 *>(row + TB / 4);
         const float nx = o.y - xi, ny = o.z - yi, nz = o.w - zi;          // x_j + (centre offset - x_i)
         sk.nx = pk2(nx, nx); sk.ny = pk2(ny, ny); sk.nz = pk2(nz, nz);
-        if (RG) {
-            // the stage's first row holds its fullest leaf: every lane runs that many pairs (a warp-uniform trip count)
-            const int trip = ((*reinterpret_cast<const int *>(stage + (s * NSL) * ROWB + TB) >> 27) & 15) + 1;
-#pragma unroll
-            for (int k = 0; k < SW / 2; k++)
-                if (k < trip) p2p_interact_pk<LS>(row + 8 * k, sk, inv_eps);
-        } else pk_row<SW, LS>(row, 0, sk, inv_eps);
+        pk_row<SW, LS>(row, 0, sk, inv_eps);
     };
     auto compute_batch = [&]() {
         cp_async_wait_all();
@@ -909,11 +883,7 @@ __global__ void tile_kernel(int nt, int nleaf, int rleaf0, int t0, const LeafDes
 template <int SW>
 static void launch_mode(pn2_ctx *h, const WalkArgs &a, int mode) {
     const unsigned grid = (unsigned)((a.nleaf + WALK_WARPS - 1) / WALK_WARPS);
-    // sparsely filled leaves (fewer than 0.82 SW particles on average): the ragged variant
-    const bool ragged = h->ragged_mode == 1 || (h->ragged_mode < 0 && (double)h->n < 0.82 * SW * (double)h->nleaf);
-    if (mode == 0 && h->prm.longshort && ragged) walk_fused_kernel<SW, true, true><<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
-    else if (mode == 0 && h->prm.longshort) walk_fused_kernel<SW, true><<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
-    else if (mode == 0 && ragged) walk_fused_kernel<SW, false, true><<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
+    if (mode == 0 && h->prm.longshort) walk_fused_kernel<SW, true><<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
     else if (mode == 0) walk_fused_kernel<SW, false><<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
     else if (mode == 3 && h->prm.longshort) walk_fused_f64_kernel<SW, true><<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
     else if (mode == 3) walk_fused_f64_kernel<SW, false><<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
