@@ -148,6 +148,13 @@ def reference_cpu_run(args, side, nranks, repeat=1, keep=False):
     import synthetic
     from oracle import pn_ref, pn_oracle
     nside_pm = max(2, int(round(side * (args.nside or args.npart_side) / args.npart_side)))
+    # The reference's LET exchange assumes that a domain meets every peer at most once through the periodic wrap: its run
+    # does not end when a domain is thinner than twice the cut-off radius (observed: 32^3 / NSIDE 32 at 12 or 16 ranks,
+    # 40^3 at 16).  Halve the rank count until every domain of src/domains.c's decomposition is wide enough.
+    import domains
+    cutoff = 4.5 * 1.25 * synthetic.BOX / nside_pm                      # src/initial.c:316-345
+    while nranks > 1 and min(float(min(d.hi[k] - d.lo[k] for k in range(3))) for d in domains.domain_boxes(nranks, synthetic.BOX)) < 2.1 * cutoff:
+        nranks //= 2
     pos = synthetic.lcdm_like(side, disp_rms=args.disp_rms, seed=12345, device="cpu").numpy()
     n = len(pos)
     mass = synthetic.particle_mass(n)

@@ -157,6 +157,7 @@ extern "C" int pn2_step_finish(pn2_ctx *h, double *d_acc) {
             CUDA_TRY(cudaEventRecord(h->ev[8], st)); CUDA_TRY(cudaEventRecord(h->ev[12], st)); CUDA_TRY(cudaEventRecord(h->ev[3], st));
         }
         if (cnt[3] & 1) { pn2_set_error("pn2: walk stack overflow (pathological particle distribution)"); return PN2_ERR_NOMEM; }
+        if (cnt[3] & 8) { pn2_set_error("pn2: a leaf's list walk did not terminate (watchdog)"); return PN2_ERR_CUDA; }
         if (cnt[3] & 4) {
             pn2_set_error("pn2: a leaf is wider than 9.8 lambda = 13.6 rs: the FP32 tile layout of the long/short split cannot hold it; use PN2_FP64");
             return PN2_ERR_ARG;

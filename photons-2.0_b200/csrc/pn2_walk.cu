@@ -26,7 +26,8 @@
 #define WALK_WARPS 4
 #endif
 #define STACK_CAP 512
-#define SRCQ_CAP 64
+#define SRCQ_CAP 256               // per-warp queue of source leaves (4-byte entries), a power of two >= 160 (see LeafWalk)
+#define PN2_WALK_WATCHDOG (1u << 20)   // steps of one sink leaf before the walk is declared stuck (counters[3] |= 8)
 #define OBUF_CAP 256              // per-warp staging of O(im) before it is flushed to a span
 #ifndef LEAF_MIN_BLOCKS
 #define LEAF_MIN_BLOCKS 5          // register cap of the leaf kernel (102 regs, 20 warps/SM): best of 4..8 measured at 256^3
@@ -174,11 +175,14 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NODE_MIN_BLOCKS) frontier_nod
     __shared__ unsigned s_stack[WALK_WARPS][STACK_CAP];
     __shared__ unsigned s_obuf[WALK_WARPS][OBUF_CAP];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int wk = blockIdx.x * WALK_WARPS + wib;
-    if (wk >= a.nwork || (a.work_count && (unsigned)wk >= *a.work_count)) return;
-    const int im = a.work[wk];
     const unsigned lt_mask = (1u << lane) - 1u;
     unsigned *stack = s_stack[wib], *obuf = s_obuf[wib];
+    // a pass over the received trees (work_count != NULL) is launched with a bounded grid that strides over the active
+    // list; otherwise the grid covers the level and the loop runs once
+    int nwork = a.nwork;
+    if (a.work_count && (int)*a.work_count < nwork) nwork = (int)*a.work_count;
+    for (int wk = blockIdx.x * WALK_WARPS + wib; wk < nwork; wk += gridDim.x * WALK_WARPS) {
+    const int im = a.work[wk];
 
     double ci[3], wi[3];
     load_geom(a.geom, im, ci, wi);
@@ -194,6 +198,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NODE_MIN_BLOCKS) frontier_nod
     unsigned first_span = 0, prev_span = 0;
     unsigned long long visits = 0;
     int err = 0;
+    unsigned nstep = 0;
     auto flush = [&]() {                     // obuf[0..osize) -> a new span
         if (osize == 0) return;
         unsigned units = 1 + (unsigned)((osize + 3) / 4);
@@ -222,47 +227,39 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NODE_MIN_BLOCKS) frontier_nod
             __syncwarp();
         }
         if (ssize == 0) break;
+        if (++nstep > PN2_WALK_WATCHDOG) { err = 8; break; }           // a walk that does not end is reported, not waited for
         int k = ssize < 32 ? ssize : 32;
         if (ssize > STACK_CAP - 64) k = 1;
         const int sbase = ssize - k;
-        int npush = 0, emit_o = 0, emit_m = 0;
-        unsigned p0 = 0, p1 = 0, o0 = 0, o1 = 0, msrc = 0;
-        int no = 0;
-        if (lane < k) {
-            const unsigned jme = stack[sbase + lane];
-            const int jm = (int)(jme & PN2_CELL_MASK);
-            const unsigned img = jme >> PN2_IMG_SHIFT, imgbits = jme & ~PN2_CELL_MASK;
-            const bool lj = jm < a.nleaf || (jm >= a.rleaf0 && jm < a.rnode0);
-            const bool remote = img != 0 || jm >= a.rleaf0;          // walk_task_*_ext rules (src/remotes.c)
-            // geometry and sons are requested together, before either is used (one round trip per step)
-            double cj[3], wj[3];
-            load_geom(a.geom, jm, cj, wj);
-            const int2 sons = lj ? make_int2(-1, -1) : *reinterpret_cast<const int2 *>(a.son + 2 * (size_t)jm);
-            if (img == 0 && jm == im) {
-                // walk(im, im): all four son combinations (src/fmm.c:429-436)
-                no = 2; o0 = (unsigned)sons.x; o1 = (unsigned)sons.y;
-            } else {
-                int pruned = 0;
-                if (remote) {
-                    // a packed node whose sons were not sent (-1) is terminal whatever this side computes
-                    if (!lj) pruned = pruned_dev(cj, wj, pc.shift[img], a.tc, a.tw, a.cutoff, a.theta, a.longshort) | (sons.x < 0) | (sons.y < 0);
-                    cj[0] += pc.shift[img][0]; cj[1] += pc.shift[img][1]; cj[2] += pc.shift[img][2];   // src/remotes.c:73-75
-                }
-                int f = accept_dev(wi, wj, ci[0] - cj[0], ci[1] - cj[1], ci[2] - cj[2], a.cutoff, a.theta, a.longshort);
-                if (f == 1) { emit_m = 1; msrc = jme; }
-                else if (f == 0) {
-                    // node x leaf: open the node; node x node: the one with the larger width sum, ties -> source
-                    // (src/fmm.c:518-527); a pruned remote node cannot be opened (src/remotes.c:351-357)
-                    bool open_i = lj || (swi > wj[0] + wj[1] + wj[2]) || pruned;
-                    if (open_i) { no = 1; o0 = jme; }
-                    else {
-                        npush = 2;
-                        p0 = (unsigned)sons.x | imgbits; p1 = (unsigned)sons.y | imgbits;
-                    }
-                }
-            }
-            emit_o = no;
+        // one straight code path for the whole warp: lanes beyond k repeat entry 0 (same addresses) and are masked out
+        const bool act = lane < k;
+        const unsigned jme = stack[sbase + (act ? lane : 0)];
+        const int jm = (int)(jme & PN2_CELL_MASK);
+        const unsigned img = jme >> PN2_IMG_SHIFT, imgbits = jme & ~PN2_CELL_MASK;
+        const bool lj = jm < a.nleaf || (jm >= a.rleaf0 && jm < a.rnode0);
+        // geometry and sons are requested together, before either is used (one round trip per step)
+        double cj[3], wj[3];
+        load_geom(a.geom, jm, cj, wj);
+        const int2 sons = lj ? make_int2(-1, -1) : *reinterpret_cast<const int2 *>(a.son + 2 * (size_t)jm);
+        int pruned = 0;
+        if (img != 0 || jm >= a.rleaf0) {                         // walk_task_*_ext rules (src/remotes.c)
+            // a packed node whose sons were not sent (-1) is terminal whatever this side computes
+            if (!lj) pruned = pruned_dev(cj, wj, pc.shift[img], a.tc, a.tw, a.cutoff, a.theta, a.longshort) | (sons.x < 0) | (sons.y < 0);
+            cj[0] += pc.shift[img][0]; cj[1] += pc.shift[img][1]; cj[2] += pc.shift[img][2];   // src/remotes.c:73-75
         }
+        const int f = accept_dev(wi, wj, ci[0] - cj[0], ci[1] - cj[1], ci[2] - cj[2], a.cutoff, a.theta, a.longshort);
+        // walk(im, im): all four son combinations (src/fmm.c:429-436): both sons inherit both sons
+        const bool self = act && img == 0 && jm == im;
+        const bool other = act && !self;
+        // node x leaf: open the node; node x node: the one with the larger width sum, ties -> source
+        // (src/fmm.c:518-527); a pruned remote node cannot be opened (src/remotes.c:351-357)
+        const bool open_i = lj || (swi > wj[0] + wj[1] + wj[2]) || pruned;
+        const int emit_m = other && f == 1;
+        const int npush = (other && f == 0 && !open_i) ? 2 : 0;
+        const int emit_o = self ? 2 : ((other && f == 0 && open_i) ? 1 : 0);
+        const unsigned o0 = self ? (unsigned)sons.x : jme, o1 = (unsigned)sons.y;
+        const unsigned p0 = (unsigned)sons.x | imgbits, p1 = (unsigned)sons.y | imgbits;
+        const unsigned msrc = jme;
         visits += k;
         __syncwarp();
         const unsigned m2 = __ballot_sync(0xffffffffu, npush == 2);
@@ -301,124 +298,111 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, NODE_MIN_BLOCKS) frontier_nod
             }
         }
     }
+    __syncwarp();
+    }   // work items of this warp
 }
 
 // ------------------------------------------------------------------------------------------------
 // Pass 2: F(leaf) = O(parent) -> source leaves -> P2P (and leaf-level M2L pairs)
 // ------------------------------------------------------------------------------------------------
-// LeafWalk resolves the frontier of ONE sink leaf, 32 stack entries per step, and appends the source leaves it
-// finds to a per-warp queue of 16-byte entries:
-//     FP32 mode (MODE 0): {tile, dx, dy, dz}  tile = leaf tile index, d = source leaf centre - sink leaf centre
-//                                             (+ image shift) in units of lambda = 2 rs sqrt(ln 2)
-//     FP64 libm / dump modes (1, 2): {first, npart, cell | image << 27, 0}
-//     FP64 tile mode (MODE 3): two int4 per entry: {tile, 0, dx (double)}, {dy, dz (doubles)}, d in units of 2 rs
-template <int MODE, int QCAP>      // QCAP = queue capacity: a power of two > (entries a consumer leaves queued, < 32) + 32
+// LeafWalk resolves the frontier of ONE sink leaf.  Source LEAVES are never tested (leaf x leaf is always a P2P pair,
+// src/fmm.c:438-451, src/remotes.c:228-240): wherever one turns up -- in the parent's list O(parent) or as the son of an
+// opened source node -- it goes straight to the per-warp QUEUE of 4-byte entries (cell | image << 27), untouched.  Only
+// source NODES sit on the stack; a step tests up to 32 of them against the sink leaf (all lanes on the same code path),
+// pushes the node sons of the opened ones and queues their leaf sons.  What a consumer needs to know about a queued
+// leaf (centre, particle count) it reads from the leaf's 32-byte descriptor when it stages the leaf's particles.
+__device__ __forceinline__ bool is_leaf_cell(const WalkArgs &a, int jm) { return jm < a.nleaf || (jm >= a.rleaf0 && jm < a.rnode0); }
+
+// TILE: the queue holds TILE indices (tile | image << 27) instead of cell ids: tile = cell for a local leaf, cell - nnode
+// for a received one (the tile arrays hold the local leaves, then the received leaves) -- translated here, 32 leaves per
+// instruction, so that the staging loop of the fused kernels has nothing to compute.
+template <int QCAP, bool TILE>   // QCAP = queue capacity, a power of two: an in-flight batch (<= 32, re-read when it lands) + < batch
+                                 // <= 32 entries left queued + <= 32 from the refill + <= 64 from a node step
 struct LeafWalk {
     SpanReader rd;
     unsigned *stack;
-    int4 *queue;
+    unsigned *queue;
     const double *sink_g;        // shared: centre, width of the sink leaf
     LeafDesc sd;
     int leaf, ssize, qtail, err;
-    unsigned nsrc, visits, npairs;
+    unsigned visits, npairs, nstep;
     unsigned pre_e;              // the next chunk of F(leaf), requested one step ahead (its latency overlaps the step)
     int pre_n;
 
-    __device__ __forceinline__ void begin(const WalkArgs &a, int leaf_, unsigned *stack_, int4 *queue_, double *sink_smem, int lane) {
+    __device__ __forceinline__ void begin(const WalkArgs &a, int leaf_, unsigned *stack_, unsigned *queue_, double *sink_smem, int lane) {
         leaf = leaf_; stack = stack_; queue = queue_; sink_g = sink_smem;
         rd.init(a.spans, a.o_head[a.parent[leaf]]);
         pre_e = 0;
         pre_n = rd.fetch(lane, pre_e);
         sd = a.desc[leaf];
         if (lane < 6) sink_smem[lane] = a.geom[6 * (size_t)leaf + lane];
-        ssize = 0; qtail = 0; err = 0; nsrc = 0; visits = 0; npairs = 0;
+        ssize = 0; qtail = 0; err = 0; visits = 0; npairs = 0; nstep = 0;
         __syncwarp();
     }
-    // one step = up to 32 entries of the stack; returns false when F(leaf) is exhausted (or the stack overflowed: err)
-    __device__ __forceinline__ bool step(const WalkArgs &a, const P2PConst &pc, int lane) {
+    // queue entry of a source leaf
+    __device__ __forceinline__ unsigned qentry(const WalkArgs &a, unsigned e) const {
+        if (!TILE) return e;
+        return (int)(e & PN2_CELL_MASK) >= a.rleaf0 ? e - (unsigned)(a.rleaf0 - a.nleaf) : e;
+    }
+    // one step; qhead = the consumer's read position, batch = the number of queued leaves it waits for.
+    // Returns false when F(leaf) is exhausted (or the stack overflowed: err).
+    __device__ __forceinline__ bool step(const WalkArgs &a, const P2PConst &pc, int lane, int qhead, int batch) {
         const unsigned lt_mask = (1u << lane) - 1u;
-        while (ssize < 32 && pre_n > 0) {
-            if (lane < pre_n) stack[ssize + lane] = pre_e;
-            ssize += pre_n;
+        if (++nstep > PN2_WALK_WATCHDOG) { err = 8; return false; }      // a walk that does not end is reported, not waited for
+        // ---- refill from the parent's list: leaves -> queue, nodes -> stack ----
+        while (ssize < 32 && pre_n > 0 && qtail - qhead < batch) {
+            const bool valid = lane < pre_n;
+            const unsigned e = pre_e;
+            const bool lj = valid && is_leaf_cell(a, (int)(e & PN2_CELL_MASK));
+            const bool nj = valid && !lj;
+            const unsigned ml = __ballot_sync(0xffffffffu, lj), mn = __ballot_sync(0xffffffffu, nj);
+            if (lj) queue[(qtail + __popc(ml & lt_mask)) & (QCAP - 1)] = qentry(a, e);
+            if (nj) stack[ssize + __popc(mn & lt_mask)] = e;
+            qtail += __popc(ml); npairs += __popc(ml); visits += __popc(ml);
+            ssize += __popc(mn);
             pre_n = rd.fetch(lane, pre_e);
             __syncwarp();
         }
-        if (ssize == 0) return false;
+        if (qtail - qhead >= batch) return true;
+        if (ssize == 0) return false;              // the loop above ended with pre_n == 0: nothing left
         int k = ssize < 32 ? ssize : 32;
         if (k > STACK_CAP - ssize) k = STACK_CAP - ssize > 0 ? STACK_CAP - ssize : 1;     // every entry can grow the stack by one
         const int sbase = ssize - k;
-        // ---- phase 1: every global load of the step is requested before any of them is used (one round trip):
-        //      a leaf's descriptor {centre, first, npart} or a node's geometry {centre, width} + sons
-        unsigned jme = 0;
-        bool lj = false;
-        double2 r0 = make_double2(0.0, 0.0), r1 = r0, r2 = r0;
-        int2 sons = make_int2(0, 0);
-        if (lane < k) {
-            jme = stack[sbase + lane];
-            const int jm = (int)(jme & PN2_CELL_MASK);
-            lj = jm < a.nleaf || (jm >= a.rleaf0 && jm < a.rnode0);
-            const double2 *rec = lj ? reinterpret_cast<const double2 *>(a.desc + jm) : reinterpret_cast<const double2 *>(a.geom + 6 * (size_t)jm);
-            r0 = rec[0]; r1 = rec[1];
-            if (!lj) { r2 = rec[2]; sons = *reinterpret_cast<const int2 *>(a.son + 2 * (size_t)jm); }
-        }
+        // ---- every global load of the step is requested before any of them is used (one round trip): geometry
+        //      {centre, width} + sons of the node.  Lanes beyond k repeat entry 0 (same addresses) and are masked out below,
+        //      so the whole step is one straight code path.
+        const bool act = lane < k;
+        const unsigned jme = stack[sbase + (act ? lane : 0)];
+        const int jm = (int)(jme & PN2_CELL_MASK);
+        const double2 *rec = reinterpret_cast<const double2 *>(a.geom + 6 * (size_t)jm);
+        const double2 r0 = rec[0], r1 = rec[1], r2 = rec[2];
+        const int2 sons = *reinterpret_cast<const int2 *>(a.son + 2 * (size_t)jm);
         visits += k;
         __syncwarp();                      // the popped entries are in registers: the stack may be overwritten from sbase
-        // ---- phase 2: decide, then compact pushes / queue entries / M2L pairs with ballots ----
-        int npush = 0, emit_p = 0, emit_m = 0;
-        unsigned p0 = 0, p1 = 0;
-        int4 ent = make_int4(0, 0, 0, 0), ent2 = ent;
-        if (lane < k) {
-            const int jm = (int)(jme & PN2_CELL_MASK);
-            const unsigned img = jme >> PN2_IMG_SHIFT, imgbits = jme & ~PN2_CELL_MASK;
-            if (lj) {
-                // leaf x leaf: always a P2P pair (src/fmm.c:438-451, src/remotes.c:228-240)
-                emit_p = 1;
-                const int dfirst = __double2loint(r1.y), dnpart = __double2hiint(r1.y);
-                if (MODE == 0) {
-                    ent.x = jm < a.nleaf ? jm : jm - a.rleaf0 + a.nleaf;
-                    ent.y = __float_as_int((float)(((r0.x + pc.shift[img][0]) - sd.c[0]) * pc.inv_len));
-                    ent.z = __float_as_int((float)(((r0.y + pc.shift[img][1]) - sd.c[1]) * pc.inv_len));
-                    ent.w = __float_as_int((float)(((r1.x + pc.shift[img][2]) - sd.c[2]) * pc.inv_len));
-                } else if (MODE == 3) {
-                    const double ox = ((r0.x + pc.shift[img][0]) - sd.c[0]) * pc.inv2rs;
-                    const double oy = ((r0.y + pc.shift[img][1]) - sd.c[1]) * pc.inv2rs;
-                    const double oz = ((r1.x + pc.shift[img][2]) - sd.c[2]) * pc.inv2rs;
-                    ent = make_int4(jm < a.nleaf ? jm : jm - a.rleaf0 + a.nleaf, 0, __double2loint(ox), __double2hiint(ox));
-                    ent2 = make_int4(__double2loint(oy), __double2hiint(oy), __double2loint(oz), __double2hiint(oz));
-                } else {
-                    ent = make_int4(dfirst, dnpart, (int)jme, 0);
-                }
-                nsrc += (unsigned)(dnpart - ((jme == (unsigned)leaf) ? 1 : 0));
-            } else {
-                double cj[3] = {r0.x, r0.y, r1.x}, wj[3] = {r1.y, r2.x, r2.y};
-                int pruned = 0;
-                if (img != 0 || jm >= a.rleaf0) {
-                    pruned = pruned_dev(cj, wj, pc.shift[img], a.tc, a.tw, a.cutoff, a.theta, a.longshort) | (sons.x < 0) | (sons.y < 0);
-                    cj[0] += pc.shift[img][0]; cj[1] += pc.shift[img][1]; cj[2] += pc.shift[img][2];
-                }
-                const int f = accept_dev(sink_g + 3, wj, sink_g[0] - cj[0], sink_g[1] - cj[1], sink_g[2] - cj[2], a.cutoff, a.theta,
-                                         a.longshort);
-                if (f == 1 || (f == 0 && pruned)) emit_m = 1;        // forced M2L on a pruned node: src/remotes.c:442
-                else if (f == 0) {
-                    npush = 2;
-                    p0 = (unsigned)sons.x | imgbits; p1 = (unsigned)sons.y | imgbits;
-                }
-            }
+        const unsigned img = jme >> PN2_IMG_SHIFT, imgbits = jme & ~PN2_CELL_MASK;
+        double cj[3] = {r0.x, r0.y, r1.x}, wj[3] = {r1.y, r2.x, r2.y};
+        int pruned = 0;
+        if (img != 0 || jm >= a.rleaf0) {
+            pruned = pruned_dev(cj, wj, pc.shift[img], a.tc, a.tw, a.cutoff, a.theta, a.longshort) | (sons.x < 0) | (sons.y < 0);
+            cj[0] += pc.shift[img][0]; cj[1] += pc.shift[img][1]; cj[2] += pc.shift[img][2];
         }
-        const unsigned m2 = __ballot_sync(0xffffffffu, npush == 2);
-        const int pos0 = sbase + 2 * __popc(m2 & lt_mask);
-        const int top = sbase + 2 * __popc(m2);
+        const int f = accept_dev(sink_g + 3, wj, sink_g[0] - cj[0], sink_g[1] - cj[1], sink_g[2] - cj[2], a.cutoff, a.theta, a.longshort);
+        const int emit_m = act && (f == 1 || (f == 0 && pruned));        // forced M2L on a pruned node: src/remotes.c:442
+        const bool open = act && f == 0 && !pruned;
+        const bool l0 = open && is_leaf_cell(a, sons.x), l1 = open && is_leaf_cell(a, sons.y);
+        const bool n0 = open && !l0, n1 = open && !l1;
+        const unsigned bn0 = __ballot_sync(0xffffffffu, n0), bn1 = __ballot_sync(0xffffffffu, n1);
+        const unsigned bl0 = __ballot_sync(0xffffffffu, l0), bl1 = __ballot_sync(0xffffffffu, l1);
+        const int top = sbase + __popc(bn0) + __popc(bn1);
         if (top > STACK_CAP) { err = 1; return false; }
-        if (npush == 2) { stack[pos0] = p0; stack[pos0 + 1] = p1; }
-        const unsigned mp = __ballot_sync(0xffffffffu, emit_p);
-        if (MODE == 3) {
-            if (emit_p) {
-                const int at = 2 * ((qtail + __popc(mp & lt_mask)) & (QCAP - 1));
-                queue[at] = ent; queue[at + 1] = ent2;
-            }
-        } else if (emit_p) queue[(qtail + __popc(mp & lt_mask)) & (QCAP - 1)] = ent;
-        qtail += __popc(mp);
-        npairs += __popc(mp);
+        const int spos = sbase + __popc(bn0 & lt_mask) + __popc(bn1 & lt_mask);
+        if (n0) stack[spos] = (unsigned)sons.x | imgbits;
+        if (n1) stack[spos + (n0 ? 1 : 0)] = (unsigned)sons.y | imgbits;
+        const int qpos = qtail + __popc(bl0 & lt_mask) + __popc(bl1 & lt_mask);
+        if (l0) queue[qpos & (QCAP - 1)] = qentry(a, (unsigned)sons.x | imgbits);
+        if (l1) queue[(qpos + (l0 ? 1 : 0)) & (QCAP - 1)] = qentry(a, (unsigned)sons.y | imgbits);
+        const int nl = __popc(bl0) + __popc(bl1);
+        qtail += nl; npairs += nl; visits += nl;
         emit_m2l_pairs(a, lane, lt_mask, emit_m, (unsigned)leaf, jme);
         ssize = top;
         __syncwarp();
@@ -431,7 +415,7 @@ template <int SW, int MODE>     // MODE 1: FP64 P2P, 2: dump lists (no arithmeti
 __global__ void __launch_bounds__(WALK_WARPS * 32) walk_leaf_kernel(WalkArgs a, P2PConst pc) {
     constexpr int NSL = 32 / SW;
     __shared__ unsigned s_stack[WALK_WARPS][STACK_CAP];
-    __shared__ int4 s_srcq[WALK_WARPS][SRCQ_CAP];
+    __shared__ unsigned s_srcq[WALK_WARPS][SRCQ_CAP];
     __shared__ double s_sink[WALK_WARPS][6];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     int leaf = blockIdx.x * WALK_WARPS + wib;
@@ -441,37 +425,40 @@ __global__ void __launch_bounds__(WALK_WARPS * 32) walk_leaf_kernel(WalkArgs a, 
         leaf = a.work[leaf];
     }
     const int q = lane / SW, j = lane % SW;
-    LeafWalk<MODE, SRCQ_CAP> w;
+    LeafWalk<SRCQ_CAP, false> w;
     w.begin(a, leaf, s_stack[wib], s_srcq[wib], s_sink[wib], lane);
     const LeafDesc sd = w.sd;
     double xd = 0, yd = 0, zd = 0, axd = 0, ayd = 0, azd = 0;
     if (MODE == 1 && j < sd.npart) { const double *p = a.pos + 3 * (size_t)(sd.first + j); xd = p[0]; yd = p[1]; zd = p[2]; }
     long dump_pos = (MODE == 2 && a.pass == 1) ? a.lst_off[leaf] : 0;
     int qhead = 0;
+    unsigned nsrc = 0;
     auto drain = [&](int limit) {          // consumes [qhead, limit)
         if (MODE == 1) {
             for (int idx = qhead + q; idx < limit; idx += NSL) {
-                const int4 e = w.queue[idx & (SRCQ_CAP - 1)];
-                const unsigned img = (unsigned)e.z >> PN2_IMG_SHIFT;
+                const unsigned e = w.queue[idx & (SRCQ_CAP - 1)];
+                const LeafDesc d = a.desc[e & PN2_CELL_MASK];
+                const unsigned img = e >> PN2_IMG_SHIFT;
                 const double sx = pc.shift[img][0], sy = pc.shift[img][1], sz = pc.shift[img][2];
-                for (int k = 0; k < e.y; k++) {
-                    const double *p = a.pos + 3 * (size_t)(e.x + k);
+                if (j == 0) nsrc += (unsigned)(d.npart - ((e == (unsigned)leaf) ? 1 : 0));
+                for (int k = 0; k < d.npart; k++) {
+                    const double *p = a.pos + 3 * (size_t)(d.first + k);
                     p2p_interact_f64(p[0] + sx, p[1] + sy, p[2] + sz, pc.mass, xd, yd, zd, axd, ayd, azd, pc.soft,
                                      pc.inv2rs, pc.longshort);
                 }
             }
         } else {
             if (a.pass == 1)
-                for (int idx = qhead + lane; idx < limit; idx += 32) a.lst_src[dump_pos + (idx - qhead)] = (unsigned)w.queue[idx & (SRCQ_CAP - 1)].z;
+                for (int idx = qhead + lane; idx < limit; idx += 32) a.lst_src[dump_pos + (idx - qhead)] = w.queue[idx & (SRCQ_CAP - 1)];
             dump_pos += limit - qhead;
         }
         qhead = limit;
         __syncwarp();
     };
-    while (w.step(a, pc, lane))
+    while (w.step(a, pc, lane, qhead, 32))
         if (w.qtail - qhead >= 32) drain(qhead + ((w.qtail - qhead) / NSL) * NSL);
     if (w.qtail > qhead) drain(w.qtail);
-    if (w.err) { if (lane == 0) atomicOr(&a.counters[3], 1ULL); return; }
+    if (w.err) { if (lane == 0) atomicOr(&a.counters[3], (unsigned long long)w.err); return; }
     if (MODE == 1) {
 #pragma unroll
         for (int m = SW; m < 32; m <<= 1) {
@@ -483,7 +470,6 @@ __global__ void __launch_bounds__(WALK_WARPS * 32) walk_leaf_kernel(WalkArgs a, 
             double *o = a.acc + 3 * (size_t)(sd.first + j);
             o[0] += axd; o[1] += ayd; o[2] += azd;
         }
-        unsigned nsrc = w.nsrc;
 #pragma unroll
         for (int m = 1; m < 32; m <<= 1) nsrc += __shfl_xor_sync(0xffffffffu, nsrc, m);
         if (lane == 0) {
@@ -510,15 +496,21 @@ __global__ void __launch_bounds__(WALK_WARPS * 32) walk_leaf_kernel(WalkArgs a, 
 #ifndef FUSED_NST
 #define FUSED_NST 8
 #endif
-template <int SW>
+// Tile layout, FP32: SW/2 pairs of 8 floats {x0 x1 y0 y1 | z0 z1 w0 w1}.  With the long/short split (LS) the weights are
+// not used (pn2_p2p.cuh), and the 8 spare bytes of pairs 0..3 carry the leaf's HEADER: its box centre (3 doubles) and its
+// particle count -- everything a sink needs to know about a source leaf arrives with the one copy of its tile.  The
+// Newtonian build keeps the weights and appends the 32-byte header to the tile.
+template <int SW, bool LS>
 struct FusedLayout {
     static constexpr int NSL = 32 / SW;
     static constexpr int NST = FUSED_NST;                 // stages per batch
     static constexpr int BATCH = NST * NSL;               // source leaves per batch (32 / 16 / 8)
-    static constexpr int TB = 16 * SW;                    // tile bytes
-    static constexpr int ROWB = TB + 16;                  // row stride: the 16 spare bytes hold the leaf's {tile, dx, dy, dz}
-                                                          // and de-conflict the NSL broadcast rows
+    static constexpr int TB = 16 * SW;                    // particle bytes of a tile
+    static constexpr int TBX = LS ? TB : TB + 32;         // tile stride in HBM and bytes staged per leaf
+    static constexpr int OFF = TBX;                       // in the staged row: {-, dx, dy, dz}, the leaf's centre offset from the sink leaf
+    static constexpr int ROWB = TBX + 16;                 // row stride (144 B with LS: the NSL broadcast rows fall into distinct banks)
     static constexpr int STAGE_BYTES = BATCH * ROWB;
+    __host__ __device__ static constexpr int hdr(int i) { return LS ? 32 * i + 24 : TB + 8 * i; }   // byte offset of header word i
 };
 
 __device__ __forceinline__ void cp_async16(unsigned dst_shared, const void *src) {
@@ -532,26 +524,27 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // block the scheduler interleaves; Poisson 256^3 83.8 vs 76.6 ms, profiles/r02n_sweep_ragged.log.  Removed.)
 template <int SW, bool LS>      // LS: with the long/short split factor g(r / 2rs)
 __global__ void __launch_bounds__(WALK_WARPS * 32, LEAF_MIN_BLOCKS) walk_fused_kernel(WalkArgs a, P2PConst pc) {
-    using FL = FusedLayout<SW>;
-    constexpr int NSL = FL::NSL, NST = FL::NST, BATCH = FL::BATCH, TB = FL::TB, ROWB = FL::ROWB;
+    using FL = FusedLayout<SW, LS>;
+    constexpr int NSL = FL::NSL, NST = FL::NST, BATCH = FL::BATCH, TB = FL::TB, TBX = FL::TBX, ROWB = FL::ROWB;
     __shared__ unsigned s_stack[WALK_WARPS][STACK_CAP];
-    __shared__ int4 s_srcq[WALK_WARPS][SRCQ_CAP];
+    __shared__ unsigned s_srcq[WALK_WARPS][SRCQ_CAP];
     __shared__ __align__(16) unsigned char s_stage[WALK_WARPS][FL::STAGE_BYTES];
     __shared__ double s_sink[WALK_WARPS][6];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    int leaf = blockIdx.x * WALK_WARPS + wib;
-    if (leaf >= a.nleaf) return;
-    if (a.work_count) {                                    // pass over the received trees: active leaves only
-        if ((unsigned)leaf >= *a.work_count) return;
-        leaf = a.work[leaf];
-    }
     const int q = lane / SW, j = lane % SW;
-    LeafWalk<0, SRCQ_CAP> w;
+    // the pass over the received trees visits the active leaves only (work_count != NULL), with a bounded grid that
+    // strides over their list; otherwise one warp per leaf and the loop runs once
+    int nitem = a.nleaf;
+    if (a.work_count && (int)*a.work_count < nitem) nitem = (int)*a.work_count;
+    for (int item = blockIdx.x * WALK_WARPS + wib; item < nitem; item += gridDim.x * WALK_WARPS) {
+    const int leaf = a.work_count ? a.work[item] : item;
+    LeafWalk<SRCQ_CAP, true> w;
     w.begin(a, leaf, s_stack[wib], s_srcq[wib], s_sink[wib], lane);
+    const LeafDesc sd = w.sd;
     // sink: slot j of the leaf's own tile (padding slots compute, but are never written)
     float xi, yi, zi;
     {
-        const float *t = a.tiles + (size_t)leaf * (4 * SW) + (j >> 1) * 8 + (j & 1);
+        const float *t = a.tiles + (size_t)leaf * (TBX / 4) + (j >> 1) * 8 + (j & 1);
         xi = t[0]; yi = t[2]; zi = t[4];
     }
     P2PSinkPk sk;
@@ -559,17 +552,26 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, LEAF_MIN_BLOCKS) walk_fused_k
     const float inv_eps = pc.inv_eps;
 
     int qhead = 0, inflight = 0;
+    unsigned nsrc = 0;
     unsigned char *stage = s_stage[wib];
     const unsigned stage_dst = (unsigned)__cvta_generic_to_shared(stage) + q * ROWB + j * 16;   // this lane's 16-byte chunk of row q
     const char *tile_src = reinterpret_cast<const char *>(a.tiles) + j * 16;
-    auto issue_batch = [&](int cnt) {      // cnt <= BATCH queue entries from qhead, a multiple of NSL
+    // the tile copies of cnt <= BATCH queue entries from qhead (a multiple of NSL): one LDS, one address, one LDGSTS per stage
+    auto issue_stage = [&](int s, unsigned te) {
+        const char *src = tile_src + (size_t)(te & PN2_CELL_MASK) * TBX;
+        cp_async16(stage_dst + s * NSL * ROWB, src);
+        if (!LS && j < 2) cp_async16(stage_dst + s * NSL * ROWB + TB, src + TB);
+    };
+    auto issue_batch = [&](int cnt) {
+        if (cnt == BATCH) {                // the queue entries first (the copies are ordered against shared-memory reads)
+            unsigned te[NST];
 #pragma unroll
-        for (int s = 0; s < NST; s++) {
-            if (s * NSL < cnt) {
-                const int4 e = w.queue[(qhead + s * NSL + q) & (SRCQ_CAP - 1)];
-                cp_async16(stage_dst + s * NSL * ROWB, tile_src + (size_t)e.x * TB);
-                if (j == 0) *reinterpret_cast<int4 *>(stage + (s * NSL + q) * ROWB + TB) = e;
-            }
+            for (int s = 0; s < NST; s++) te[s] = w.queue[(qhead + s * NSL + q) & (SRCQ_CAP - 1)];
+#pragma unroll
+            for (int s = 0; s < NST; s++) issue_stage(s, te[s]);
+        } else {
+#pragma unroll 1
+            for (int s = 0; s * NSL < cnt; s++) issue_stage(s, w.queue[(qhead + s * NSL + q) & (SRCQ_CAP - 1)]);
         }
         cp_async_commit();
         inflight = cnt;
@@ -577,13 +579,32 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, LEAF_MIN_BLOCKS) walk_fused_k
     };
     auto compute_stage = [&](int s) {
         const float *row = reinterpret_cast<const float *>(stage + (s * NSL + q) * ROWB);
-        const float4 o = *reinterpret_cast<const float4 *>(row + TB / 4);
+        const float4 o = *reinterpret_cast<const float4 *>(row + FL::OFF / 4);
         const float nx = o.y - xi, ny = o.z - yi, nz = o.w - zi;          // x_j + (centre offset - x_i)
         sk.nx = pk2(nx, nx); sk.ny = pk2(ny, ny); sk.nz = pk2(nz, nz);
         pk_row<SW, LS>(row, 0, sk, inv_eps);
     };
     auto compute_batch = [&]() {
         cp_async_wait_all();
+        __syncwarp();
+        // lane r resolves row r from the header that came with the tile: centre offset of the source leaf from the sink
+        // leaf (FP64, rounded once; units of lambda) and the leaf's particle count
+        if (lane < inflight) {
+            const unsigned te = w.queue[(qhead - inflight + lane) & (SRCQ_CAP - 1)];
+            unsigned char *row = stage + lane * ROWB;
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (te != (unsigned)a.pad_tile) {
+                const unsigned img = te >> PN2_IMG_SHIFT;
+                const double cx = *reinterpret_cast<const double *>(row + FL::hdr(0));
+                const double cy = *reinterpret_cast<const double *>(row + FL::hdr(1));
+                const double cz = *reinterpret_cast<const double *>(row + FL::hdr(2));
+                o.y = (float)(((cx + pc.shift[img][0]) - sd.c[0]) * pc.inv_len);
+                o.z = (float)(((cy + pc.shift[img][1]) - sd.c[1]) * pc.inv_len);
+                o.w = (float)(((cz + pc.shift[img][2]) - sd.c[2]) * pc.inv_len);
+                nsrc += (unsigned)(*reinterpret_cast<const int *>(row + FL::hdr(3)) - ((te == (unsigned)leaf) ? 1 : 0));
+            }
+            *reinterpret_cast<float4 *>(row + FL::OFF) = o;
+        }
         __syncwarp();
         if (inflight == BATCH) {           // the common case as one straight-line block: stages overlap in the schedule
 #pragma unroll
@@ -599,20 +620,20 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, LEAF_MIN_BLOCKS) walk_fused_k
     // earlier, request the tiles of the new batch, walk on
     bool walking = true;
     while (true) {
-        while (walking && w.qtail - qhead < BATCH) walking = w.step(a, pc, lane);
+        while (walking && w.qtail - qhead < BATCH) walking = w.step(a, pc, lane, qhead, BATCH);
         if (inflight) compute_batch();
         const int avail = w.qtail - qhead;
         if (avail == 0 || w.err) break;                              // walking implies avail >= BATCH
         int cnt = BATCH;
         if (avail < BATCH) {                                           // the last batch: pad its last stage with the padding tile
             cnt = ((avail + NSL - 1) / NSL) * NSL;
-            if (lane < cnt - avail) w.queue[(w.qtail + lane) & (SRCQ_CAP - 1)] = make_int4(a.pad_tile, 0, 0, 0);
+            if (lane < cnt - avail) w.queue[(w.qtail + lane) & (SRCQ_CAP - 1)] = (unsigned)a.pad_tile;
             w.qtail = qhead + cnt;
             __syncwarp();
         }
         issue_batch(cnt);
     }
-    if (w.err) { if (lane == 0) atomicOr(&a.counters[3], 1ULL); return; }
+    if (w.err) { if (lane == 0) atomicOr(&a.counters[3], (unsigned long long)w.err); continue; }
 
     float ax, ay, az, hi;
     unpk2(sk.ax, ax, hi); ax += hi;
@@ -624,13 +645,11 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, LEAF_MIN_BLOCKS) walk_fused_k
         ay += __shfl_xor_sync(0xffffffffu, ay, m);
         az += __shfl_xor_sync(0xffffffffu, az, m);
     }
-    const LeafDesc sd = w.sd;
     if (q == 0 && j < sd.npart) {
         const double sc = pc.mass * pc.inv_len * pc.inv_len;
         double *o = a.acc + 3 * (size_t)(sd.first + j);
         o[0] += (double)ax * sc; o[1] += (double)ay * sc; o[2] += (double)az * sc;
     }
-    unsigned nsrc = w.nsrc;
 #pragma unroll
     for (int m = 1; m < 32; m <<= 1) nsrc += __shfl_xor_sync(0xffffffffu, nsrc, m);
     if (lane == 0) {
@@ -638,6 +657,8 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, LEAF_MIN_BLOCKS) walk_fused_k
         atomicAdd(&a.counters[2], (unsigned long long)w.npairs);
         atomicAdd(&a.counters[4], (unsigned long long)w.visits);
     }
+    __syncwarp();
+    }   // leaves of this warp
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -656,14 +677,19 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, LEAF_MIN_BLOCKS) walk_fused_k
 #ifndef F64_MAGIC
 #define F64_MAGIC 1
 #endif
-template <int SW>
+// FP64 tiles: SW slots of {x, y, z, w} doubles.  With the long/short split the weight is not read, and the w of slots
+// 0..3 carries the leaf's header {centre x, y, z, particle count}; the Newtonian build appends the 32-byte header.
+template <int SW, bool LS>
 struct Fused64Layout {
     static constexpr int NSL = 32 / SW;
     static constexpr int NST = F64_NST;
     static constexpr int BATCH = NST * NSL;               // source leaves per batch (16 / 8 / 4)
-    static constexpr int TB = 32 * SW;                    // tile bytes
-    static constexpr int ROWB = TB + 32;                  // + {dx, dy, dz, -} of the leaf
+    static constexpr int TB = 32 * SW;                    // particle bytes of a tile
+    static constexpr int TBX = LS ? TB : TB + 32;         // tile stride in HBM and bytes staged per leaf
+    static constexpr int OFF = TBX;                       // in the staged row: {-, dx, dy, dz} (doubles): centre offset from the sink leaf
+    static constexpr int ROWB = LS ? TBX + 32 : TBX + 64; // row stride (288 / 544 / 1056 B with LS: the NSL broadcast rows fall into distinct banks)
     static constexpr int STAGE_BYTES = BATCH * ROWB;
+    __host__ __device__ static constexpr int hdr(int i) { return LS ? 32 * i + 24 : TB + 8 * i; }
 };
 __device__ __forceinline__ double pn2_rsqrt64(double x) {   // MUFU.RSQ64H: ~20-bit seed
     double y;
@@ -719,28 +745,27 @@ __device__ __forceinline__ void p2p_interact_tab64(const double *slot, P2PSink64
 
 template <int SW, bool LS>
 __global__ void __launch_bounds__(WALK_WARPS * 32, F64_MIN_BLOCKS) walk_fused_f64_kernel(WalkArgs a, P2PConst pc) {
-    using FL = Fused64Layout<SW>;
-    constexpr int NSL = FL::NSL, NST = FL::NST, BATCH = FL::BATCH, TB = FL::TB, ROWB = FL::ROWB;
+    using FL = Fused64Layout<SW, LS>;
+    constexpr int NSL = FL::NSL, NST = FL::NST, BATCH = FL::BATCH, TB = FL::TB, TBX = FL::TBX, ROWB = FL::ROWB;
     __shared__ unsigned s_stack[WALK_WARPS][STACK_CAP];
-    __shared__ int4 s_srcq[WALK_WARPS][2 * SRCQ_CAP];
+    __shared__ unsigned s_srcq[WALK_WARPS][SRCQ_CAP];
     __shared__ __align__(16) unsigned char s_stage[WALK_WARPS][FL::STAGE_BYTES];
     __shared__ double s_sink[WALK_WARPS][6];
     __shared__ __align__(128) double s_gtab[PN2_GTAB_DEG + 1][PN2_GTAB_K];
     for (int i = threadIdx.x; i < (PN2_GTAB_DEG + 1) * PN2_GTAB_K; i += blockDim.x) (&s_gtab[0][0])[i] = a.gtab[i];
     __syncthreads();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    int leaf = blockIdx.x * WALK_WARPS + wib;
-    if (leaf >= a.nleaf) return;
-    if (a.work_count) {
-        if ((unsigned)leaf >= *a.work_count) return;
-        leaf = a.work[leaf];
-    }
     const int q = lane / SW, j = lane % SW;
-    LeafWalk<3, SRCQ_CAP> w;
+    int nitem = a.nleaf;
+    if (a.work_count && (int)*a.work_count < nitem) nitem = (int)*a.work_count;
+    for (int item = blockIdx.x * WALK_WARPS + wib; item < nitem; item += gridDim.x * WALK_WARPS) {
+    const int leaf = a.work_count ? a.work[item] : item;
+    LeafWalk<SRCQ_CAP, true> w;
     w.begin(a, leaf, s_stack[wib], s_srcq[wib], s_sink[wib], lane);
+    const LeafDesc sd = w.sd;
     double xi, yi, zi;
     {
-        const double *t = a.tiles64 + ((size_t)leaf * SW + j) * 4;
+        const double *t = reinterpret_cast<const double *>(reinterpret_cast<const char *>(a.tiles64) + (size_t)leaf * TBX) + j * 4;
         xi = t[0]; yi = t[1]; zi = t[2];
     }
     P2PSink64 sk;
@@ -750,6 +775,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, F64_MIN_BLOCKS) walk_fused_f6
     const double eps2 = eps * eps, inv_eps = eps > 0.0 ? 1.0 / eps : 1e100;
 
     int qhead = 0, inflight = 0;
+    unsigned nsrc = 0;
     unsigned char *stage = s_stage[wib];
     const unsigned stage_dst = (unsigned)__cvta_generic_to_shared(stage) + q * ROWB + j * 16;   // first of this lane's two chunks
     const char *tile_src = reinterpret_cast<const char *>(a.tiles64) + j * 16;
@@ -757,15 +783,11 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, F64_MIN_BLOCKS) walk_fused_f6
 #pragma unroll
         for (int s = 0; s < NST; s++) {
             if (s * NSL < cnt) {
-                const int qi = 2 * ((qhead + s * NSL + q) & (SRCQ_CAP - 1));
-                const int4 e0 = w.queue[qi];
-                const char *src = tile_src + (size_t)e0.x * TB;
+                const unsigned te = w.queue[(qhead + s * NSL + q) & (SRCQ_CAP - 1)];
+                const char *src = tile_src + (size_t)(te & PN2_CELL_MASK) * TBX;
                 cp_async16(stage_dst + s * NSL * ROWB, src);
                 cp_async16(stage_dst + s * NSL * ROWB + SW * 16, src + SW * 16);
-                if (j == 0) {
-                    int4 *hd = reinterpret_cast<int4 *>(stage + (s * NSL + q) * ROWB + TB);
-                    hd[0] = e0; hd[1] = w.queue[qi + 1];
-                }
+                if (!LS && j < 2) cp_async16(stage_dst + s * NSL * ROWB + TB, src + TB);
             }
         }
         cp_async_commit();
@@ -774,13 +796,28 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, F64_MIN_BLOCKS) walk_fused_f6
     };
     auto compute_stage = [&](int s) {
         const double *row = reinterpret_cast<const double *>(stage + (s * NSL + q) * ROWB);
-        const double *hd = row + TB / 8;
+        const double *hd = row + FL::OFF / 8;
         sk.nx = hd[1] - xi; sk.ny = hd[2] - yi; sk.nz = hd[3] - zi;
 #pragma unroll
         for (int k = 0; k < SW; k++) p2p_interact_tab64<LS>(row + 4 * k, sk, k & 1, eps2, inv_eps, s_gtab);
     };
     auto compute_batch = [&]() {
         cp_async_wait_all();
+        __syncwarp();
+        if (lane < inflight) {             // lane r resolves row r from the header that came with the tile
+            const unsigned te = w.queue[(qhead - inflight + lane) & (SRCQ_CAP - 1)];
+            unsigned char *row = stage + lane * ROWB;
+            double ox = 0.0, oy = 0.0, oz = 0.0;
+            if (te != (unsigned)a.pad_tile) {
+                const unsigned img = te >> PN2_IMG_SHIFT;
+                ox = ((*reinterpret_cast<const double *>(row + FL::hdr(0)) + pc.shift[img][0]) - sd.c[0]) * pc.inv2rs;
+                oy = ((*reinterpret_cast<const double *>(row + FL::hdr(1)) + pc.shift[img][1]) - sd.c[1]) * pc.inv2rs;
+                oz = ((*reinterpret_cast<const double *>(row + FL::hdr(2)) + pc.shift[img][2]) - sd.c[2]) * pc.inv2rs;
+                nsrc += (unsigned)(*reinterpret_cast<const int *>(row + FL::hdr(3)) - ((te == (unsigned)leaf) ? 1 : 0));
+            }
+            double *hd = reinterpret_cast<double *>(row + FL::OFF);
+            hd[1] = ox; hd[2] = oy; hd[3] = oz;
+        }
         __syncwarp();
 #pragma unroll 1
         for (int s = 0; s * NSL < inflight; s++) compute_stage(s);
@@ -789,23 +826,20 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, F64_MIN_BLOCKS) walk_fused_f6
     };
     bool walking = true;
     while (true) {
-        while (walking && w.qtail - qhead < BATCH) walking = w.step(a, pc, lane);
+        while (walking && w.qtail - qhead < BATCH) walking = w.step(a, pc, lane, qhead, BATCH);
         if (inflight) compute_batch();
         const int avail = w.qtail - qhead;
         if (avail == 0 || w.err) break;
         int cnt = BATCH;
         if (avail < BATCH) {
             cnt = ((avail + NSL - 1) / NSL) * NSL;
-            if (lane < cnt - avail) {
-                const int at = 2 * ((w.qtail + lane) & (SRCQ_CAP - 1));
-                w.queue[at] = make_int4(a.pad_tile, 0, 0, 0); w.queue[at + 1] = make_int4(0, 0, 0, 0);
-            }
+            if (lane < cnt - avail) w.queue[(w.qtail + lane) & (SRCQ_CAP - 1)] = (unsigned)a.pad_tile;
             w.qtail = qhead + cnt;
             __syncwarp();
         }
         issue_batch(cnt);
     }
-    if (w.err) { if (lane == 0) atomicOr(&a.counters[3], 1ULL); return; }
+    if (w.err) { if (lane == 0) atomicOr(&a.counters[3], (unsigned long long)w.err); continue; }
 
     double ax = sk.ax[0] + sk.ax[1], ay = sk.ay[0] + sk.ay[1], az = sk.az[0] + sk.az[1];
 #pragma unroll
@@ -814,13 +848,11 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, F64_MIN_BLOCKS) walk_fused_f6
         ay += __shfl_xor_sync(0xffffffffu, ay, m);
         az += __shfl_xor_sync(0xffffffffu, az, m);
     }
-    const LeafDesc sd = w.sd;
     if (q == 0 && j < sd.npart) {
         const double sc = pc.mass * pc.inv2rs * pc.inv2rs;
         double *o = a.acc + 3 * (size_t)(sd.first + j);
         o[0] += ax * sc; o[1] += ay * sc; o[2] += az * sc;
     }
-    unsigned nsrc = w.nsrc;
 #pragma unroll
     for (int m = 1; m < 32; m <<= 1) nsrc += __shfl_xor_sync(0xffffffffu, nsrc, m);
     if (lane == 0) {
@@ -828,25 +860,34 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, F64_MIN_BLOCKS) walk_fused_f6
         atomicAdd(&a.counters[2], (unsigned long long)w.npairs);
         atomicAdd(&a.counters[4], (unsigned long long)w.visits);
     }
+    __syncwarp();
+    }   // leaves of this warp
 }
 
 // FP64 tiles: slot j of tile t <- (pos - leaf centre) / (2 rs) of particle j, w = 1; padding far away with w = 0
-template <int SW>
+template <int SW, bool LS>
 __global__ void tile64_kernel(int nt, int nleaf, int rleaf0, const LeafDesc *__restrict__ desc, const double *__restrict__ pos,
                               double inv2rs, double *__restrict__ tiles) {
+    using FL = Fused64Layout<SW, LS>;
     const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const int tile = (int)(t / SW), j = (int)(t % SW);
     if (tile > nt) return;
     double4 p = make_double4(1e4, 1e4, 1e4, 0.0);
+    double hdr = 0.0;                                       // header word j (j < 4): centre x, y, z, particle count
     if (tile < nt) {
         const LeafDesc d = desc[tile < nleaf ? tile : tile - nleaf + rleaf0];
         if (j < d.npart) {
             const double *x = pos + 3 * (size_t)(d.first + j);
             p = make_double4((x[0] - d.c[0]) * inv2rs, (x[1] - d.c[1]) * inv2rs, (x[2] - d.c[2]) * inv2rs, 1.0);
         }
+        if (j < 3) hdr = d.c[j];
+        else if (j == 3) hdr = __hiloint2double(0, d.npart);
     }
-    double2 *o = reinterpret_cast<double2 *>(tiles + ((size_t)tile * SW + j) * 4);
-    o[0] = make_double2(p.x, p.y); o[1] = make_double2(p.z, p.w);
+    char *base = reinterpret_cast<char *>(tiles) + (size_t)tile * FL::TBX;
+    double *o = reinterpret_cast<double *>(base) + 4 * j;
+    o[0] = p.x; o[1] = p.y; o[2] = p.z;
+    if (!LS) o[3] = p.w;
+    if (j < 4) *reinterpret_cast<double *>(base + FL::hdr(j)) = hdr;
 }
 
 // Leaf tiles (FP32 mode): slot j of tile t <- particle j of the leaf, packed-pair layout; tile nt = all padding.
@@ -857,14 +898,16 @@ __global__ void tile64_kernel(int nt, int nleaf, int rleaf0, const LeafDesc *__r
 // are listed only when their boxes are closer than the cut-off, 2.71 lambda).  Wider leaves (NSIDE far finer than the
 // particle spacing) are reported instead of being evaluated wrongly: counters[3] |= 4.
 #define PN2_PAD_SAFE 4.9f
-template <int SW>
+template <int SW, bool LS>
 __global__ void tile_kernel(int nt, int nleaf, int rleaf0, int t0, const LeafDesc *__restrict__ desc, const double *__restrict__ pos,
-                            const float4 *__restrict__ rel, double inv_len, float *__restrict__ tiles, int longshort,
+                            const float4 *__restrict__ rel, double inv_len, float *__restrict__ tiles,
                             unsigned long long *__restrict__ counters) {
+    using FL = FusedLayout<SW, LS>;
     const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const int tile = t0 + (int)(t / SW), j = (int)(t % SW);
     if (tile > nt) return;
     float4 p = make_float4(PN2_PAD_COORD, PN2_PAD_COORD, PN2_PAD_COORD, 0.f);
+    double hdr = 0.0;                                       // header word j (j < 4): centre x, y, z, particle count; zeros for the padding tile
     if (tile < nt) {
         const LeafDesc d = desc[tile < nleaf ? tile : tile - nleaf + rleaf0];
         if (j < d.npart) {
@@ -873,16 +916,23 @@ __global__ void tile_kernel(int nt, int nleaf, int rleaf0, int t0, const LeafDes
                 const double *x = pos + 3 * (size_t)(d.first + j);
                 p = make_float4((float)((x[0] - d.c[0]) * inv_len), (float)((x[1] - d.c[1]) * inv_len), (float)((x[2] - d.c[2]) * inv_len), 1.f);
             } else p = rel[d.first + j];                     // a received leaf: its sender shipped these very values
-            if (longshort && fmaxf(fmaxf(fabsf(p.x), fabsf(p.y)), fabsf(p.z)) > PN2_PAD_SAFE) atomicOr(&counters[3], 4ULL);
+            if (LS && fmaxf(fmaxf(fabsf(p.x), fabsf(p.y)), fabsf(p.z)) > PN2_PAD_SAFE) atomicOr(&counters[3], 4ULL);
         }
+        if (j < 3) hdr = d.c[j];
+        else if (j == 3) hdr = __hiloint2double(0, d.npart);
     }
-    float *o = tiles + (size_t)tile * (4 * SW) + (j >> 1) * 8 + (j & 1);
-    o[0] = p.x; o[2] = p.y; o[4] = p.z; o[6] = p.w;
+    char *base = reinterpret_cast<char *>(tiles) + (size_t)tile * FL::TBX;
+    float *o = reinterpret_cast<float *>(base) + (j >> 1) * 8 + (j & 1);
+    o[0] = p.x; o[2] = p.y; o[4] = p.z;
+    if (!LS) o[6] = p.w;
+    if (j < 4) *reinterpret_cast<double *>(base + FL::hdr(j)) = hdr;
 }
 
 template <int SW>
 static void launch_mode(pn2_ctx *h, const WalkArgs &a, int mode) {
-    const unsigned grid = (unsigned)((a.nleaf + WALK_WARPS - 1) / WALK_WARPS);
+    unsigned grid = (unsigned)((a.nleaf + WALK_WARPS - 1) / WALK_WARPS);
+    const unsigned gcap = (unsigned)(h->sm_count > 0 ? h->sm_count : 148) * LEAF_MIN_BLOCKS * 4;
+    if (a.work_count && (mode == 0 || mode == 3) && grid > gcap) grid = gcap;      // active leaves only: a bounded grid strides over their list
     if (mode == 0 && h->prm.longshort) walk_fused_kernel<SW, true><<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
     else if (mode == 0) walk_fused_kernel<SW, false><<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
     else if (mode == 3 && h->prm.longshort) walk_fused_f64_kernel<SW, true><<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
@@ -941,7 +991,12 @@ int pn2_walk_frontiers(pn2_ctx *h) {
             a.work = h->level_nodes.p + h->level_off[lev];
         }
         a.nwork = cnt;
-        frontier_node_kernel<<<(cnt + WALK_WARPS - 1) / WALK_WARPS, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
+        unsigned grid = (unsigned)((cnt + WALK_WARPS - 1) / WALK_WARPS);
+        // the active list of a pass over the received trees is short (cells near the domain surface): a few waves of CTAs
+        // stride over it instead of one CTA per four cells of the level, most of which would exit at once
+        const unsigned gcap = (unsigned)(h->sm_count > 0 ? h->sm_count : 148) * NODE_MIN_BLOCKS * 2;
+        if (h->walk_active && grid > gcap) grid = gcap;
+        frontier_node_kernel<<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
         h->launches++;
     }
     KERNEL_CHECK();
@@ -963,16 +1018,19 @@ int pn2_walk_fused(pn2_ctx *h, int dump) {
     if (mode == 3) {
         const int sw = ml <= 8 ? 8 : (ml <= 16 ? 16 : 32);
         const int nt = h->nleaf + h->nrl;
-        PN2_TRY(h->tiles64.ensure(((size_t)nt + 1) * 4 * sw));
+        const bool ls = h->prm.longshort != 0;
+        PN2_TRY(h->tiles64.ensure(((size_t)nt + 1) * (4 * sw + (ls ? 0 : 4))));
         if (!h->gtab.p) {
             PN2_TRY(h->gtab.ensure((PN2_GTAB_DEG + 1) * PN2_GTAB_K));
             CUDA_TRY(cudaMemcpyAsync(h->gtab.p, PN2_GTAB, sizeof PN2_GTAB, cudaMemcpyHostToDevice, h->stream));
         }
         const long nthr = ((long)nt + 1) * sw;
         const unsigned g = (unsigned)((nthr + 255) / 256);
-        if (sw == 8) tile64_kernel<8><<<g, 256, 0, h->stream>>>(nt, h->nleaf, h->ncell, h->desc.p, h->pos.p, h->pc.inv2rs, h->tiles64.p);
-        else if (sw == 16) tile64_kernel<16><<<g, 256, 0, h->stream>>>(nt, h->nleaf, h->ncell, h->desc.p, h->pos.p, h->pc.inv2rs, h->tiles64.p);
-        else tile64_kernel<32><<<g, 256, 0, h->stream>>>(nt, h->nleaf, h->ncell, h->desc.p, h->pos.p, h->pc.inv2rs, h->tiles64.p);
+#define PN2_TILE64_LAUNCH(SWV, LSV) tile64_kernel<SWV, LSV><<<g, 256, 0, h->stream>>>(nt, h->nleaf, h->ncell, h->desc.p, h->pos.p, h->pc.inv2rs, h->tiles64.p)
+        if (sw == 8) { if (ls) PN2_TILE64_LAUNCH(8, true); else PN2_TILE64_LAUNCH(8, false); }
+        else if (sw == 16) { if (ls) PN2_TILE64_LAUNCH(16, true); else PN2_TILE64_LAUNCH(16, false); }
+        else { if (ls) PN2_TILE64_LAUNCH(32, true); else PN2_TILE64_LAUNCH(32, false); }
+#undef PN2_TILE64_LAUNCH
         h->launches++;
         a.tiles64 = h->tiles64.p; a.gtab = h->gtab.p; a.pad_tile = nt;
     }
@@ -981,15 +1039,18 @@ int pn2_walk_fused(pn2_ctx *h, int dump) {
         // (the pass over the local roots); the pass over the received trees appends its tiles and a new padding tile.
         const int sw = ml <= 8 ? 8 : (ml <= 16 ? 16 : 32);
         const int nt = h->nleaf + h->nrl;
-        const size_t need = ((size_t)nt + 1) * 4 * sw;
+        const bool ls = h->prm.longshort != 0;
+        const size_t need = ((size_t)nt + 1) * (4 * sw + (ls ? 0 : 8));  // floats: 16 SW bytes per tile (+ the 32-byte header without the split)
         const bool grows = need > h->tiles.cap;                         // a new buffer: every tile again
         PN2_TRY(h->tiles.ensure(need));
         const int t0 = (!grows && h->tiles_built_for == h->step_serial && h->nrl > 0) ? h->nleaf : 0;
         const long nthr = ((long)nt + 1 - t0) * sw;
         const unsigned g = (unsigned)((nthr + 255) / 256);
-        if (sw == 8) tile_kernel<8><<<g, 256, 0, h->stream>>>(nt, h->nleaf, h->ncell, t0, h->desc.p, h->pos.p, h->rel.p, h->pc.inv_len, h->tiles.p, h->prm.longshort, h->counters.p);
-        else if (sw == 16) tile_kernel<16><<<g, 256, 0, h->stream>>>(nt, h->nleaf, h->ncell, t0, h->desc.p, h->pos.p, h->rel.p, h->pc.inv_len, h->tiles.p, h->prm.longshort, h->counters.p);
-        else tile_kernel<32><<<g, 256, 0, h->stream>>>(nt, h->nleaf, h->ncell, t0, h->desc.p, h->pos.p, h->rel.p, h->pc.inv_len, h->tiles.p, h->prm.longshort, h->counters.p);
+#define PN2_TILE_LAUNCH(SWV, LSV) tile_kernel<SWV, LSV><<<g, 256, 0, h->stream>>>(nt, h->nleaf, h->ncell, t0, h->desc.p, h->pos.p, h->rel.p, h->pc.inv_len, h->tiles.p, h->counters.p)
+        if (sw == 8) { if (ls) PN2_TILE_LAUNCH(8, true); else PN2_TILE_LAUNCH(8, false); }
+        else if (sw == 16) { if (ls) PN2_TILE_LAUNCH(16, true); else PN2_TILE_LAUNCH(16, false); }
+        else { if (ls) PN2_TILE_LAUNCH(32, true); else PN2_TILE_LAUNCH(32, false); }
+#undef PN2_TILE_LAUNCH
         h->launches++;
         h->tiles_built_for = h->step_serial;
         a.tiles = h->tiles.p; a.pad_tile = nt;
