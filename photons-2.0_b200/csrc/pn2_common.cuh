@@ -112,6 +112,7 @@ struct pn2_ctx {
     bool use_lflags = false;
     DBuf<int> level_nodes;     // node cell ids grouped by depth
     std::vector<int> level_off;   // [nlevel + 1]
+    std::vector<int> leaf_off;    // Mode B: [nlevel + 1]: the leaf sons of the nodes of level l are the leaves leaf_off[l] .. leaf_off[l + 1] - 1, in the order of their parents
     // ---- received LET (Mode A) ----
     int r_nnode = 0, r_nbody = 0;
     DBuf<LeafDesc> r_desc;

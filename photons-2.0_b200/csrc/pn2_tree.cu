@@ -527,6 +527,7 @@ static int tree_build_once(pn2_ctx *h, const double *d_pos_in, int n, const pn2_
     h->nleaf = h->nnode = h->ncell = h->nlevel = 0;
     h->nrl = h->nrn = h->nrp = 0;
     h->level_off.assign(1, 0);
+    h->leaf_off.clear();
     PN2_TRY(h->pos.ensure(3 * (size_t)n + 3));
     PN2_TRY(h->acc.ensure(3 * (size_t)n + 3)); PN2_TRY(h->rel.ensure((size_t)n + 1));
     PN2_TRY(h->order.ensure(n + 1)); PN2_TRY(h->b_idx2.ensure(n + 1));
@@ -591,7 +592,7 @@ static int tree_build_once(pn2_ctx *h, const double *d_pos_in, int n, const pn2_
     unsigned *qc = h->b_qc.p, *qo = h->b_qc2.p;
     int *sg = h->b_seg.p, *so = h->b_seg2.p;
     int node0 = 0, cnt = 1, nleaf = 0, level = 0;
-    std::vector<int> level_off(1, 0);
+    std::vector<int> level_off(1, 0), leaf_off(1, 0);
 
     // ---- deferred levels (see top_level_kernel): every level relabels the particles where the Morton sort put them; one
     //      stable sort on the start position of every particle's leaf then gives the tree order (Morton order inside a
@@ -625,6 +626,7 @@ static int tree_build_once(pn2_ctx *h, const double *d_pos_in, int n, const pn2_
             level_off.push_back(node0);
             cnt = hs[0];
             nleaf = hs[1];
+            leaf_off.push_back(nleaf);
             level++;
         }
         // tree order: sort the Morton ranks by the start position of their leaf (stable), then fetch positions / caller indices
@@ -663,6 +665,7 @@ static int tree_build_once(pn2_ctx *h, const double *d_pos_in, int n, const pn2_
         level_off.push_back(node0);
         cnt = hs[0];
         nleaf = hs[1];
+        leaf_off.push_back(nleaf);
         level++;
     }
     if (!deferred) {
@@ -673,6 +676,7 @@ static int tree_build_once(pn2_ctx *h, const double *d_pos_in, int n, const pn2_
     if ((size_t)nleaf + nnode >= (1u << PN2_IMG_SHIFT)) { pn2_set_error("pn2: more than 2^27 cells on one device"); return PN2_ERR_ARG; }
     h->nleaf = nleaf; h->nnode = nnode; h->ncell = nleaf + nnode; h->nlevel = level;
     h->level_off = level_off;
+    h->leaf_off = leaf_off;
     h->first_leaf = 0; h->last_leaf = nleaf; h->first_node = nleaf; h->last_node = nleaf + nnode - 1;
     size_t nc = (size_t)h->ncell;
     PN2_TRY(h->geom.ensure(6 * nc + 6)); PN2_TRY(h->son.ensure(2 * nc + 2)); PN2_TRY(h->desc.ensure(nc + 1));

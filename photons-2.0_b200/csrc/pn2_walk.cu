@@ -71,6 +71,7 @@ struct WalkArgs {
     unsigned *next_count;
     int *leaf_work;                    // node kernel: active sink leaves (or NULL)
     unsigned *leaf_count;
+    int item_lo, item_hi;              // leaf kernels: the sink leaves item_lo .. item_hi - 1 (0 .. nleaf - 1 unless set)
 };
 
 // acceptance(), src/fmm.c:267-326: 0 open, 1 accept, -1 drop.  Same expressions in the same order (this file is
@@ -534,9 +535,9 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, LEAF_MIN_BLOCKS) walk_fused_k
     const int q = lane / SW, j = lane % SW;
     // the pass over the received trees visits the active leaves only (work_count != NULL), with a bounded grid that
     // strides over their list; otherwise one warp per leaf and the loop runs once
-    int nitem = a.nleaf;
+    int item0 = a.item_lo, nitem = a.item_hi;
     if (a.work_count && (int)*a.work_count < nitem) nitem = (int)*a.work_count;
-    for (int item = blockIdx.x * WALK_WARPS + wib; item < nitem; item += gridDim.x * WALK_WARPS) {
+    for (int item = item0 + blockIdx.x * WALK_WARPS + wib; item < nitem; item += gridDim.x * WALK_WARPS) {
     const int leaf = a.work_count ? a.work[item] : item;
     LeafWalk<SRCQ_CAP, true> w;
     w.begin(a, leaf, s_stack[wib], s_srcq[wib], s_sink[wib], lane);
@@ -756,9 +757,9 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, F64_MIN_BLOCKS) walk_fused_f6
     __syncthreads();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int q = lane / SW, j = lane % SW;
-    int nitem = a.nleaf;
+    int item0 = a.item_lo, nitem = a.item_hi;
     if (a.work_count && (int)*a.work_count < nitem) nitem = (int)*a.work_count;
-    for (int item = blockIdx.x * WALK_WARPS + wib; item < nitem; item += gridDim.x * WALK_WARPS) {
+    for (int item = item0 + blockIdx.x * WALK_WARPS + wib; item < nitem; item += gridDim.x * WALK_WARPS) {
     const int leaf = a.work_count ? a.work[item] : item;
     LeafWalk<SRCQ_CAP, true> w;
     w.begin(a, leaf, s_stack[wib], s_srcq[wib], s_sink[wib], lane);
@@ -929,17 +930,28 @@ __global__ void tile_kernel(int nt, int nleaf, int rleaf0, int t0, const LeafDes
 }
 
 template <int SW>
-static void launch_mode(pn2_ctx *h, const WalkArgs &a, int mode) {
-    unsigned grid = (unsigned)((a.nleaf + WALK_WARPS - 1) / WALK_WARPS);
-    const unsigned gcap = (unsigned)(h->sm_count > 0 ? h->sm_count : 148) * LEAF_MIN_BLOCKS * 4;
-    if (a.work_count && (mode == 0 || mode == 3) && grid > gcap) grid = gcap;      // active leaves only: a bounded grid strides over their list
-    if (mode == 0 && h->prm.longshort) walk_fused_kernel<SW, true><<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
-    else if (mode == 0) walk_fused_kernel<SW, false><<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
-    else if (mode == 3 && h->prm.longshort) walk_fused_f64_kernel<SW, true><<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
-    else if (mode == 3) walk_fused_f64_kernel<SW, false><<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
-    else if (mode == 1) walk_leaf_kernel<SW, 1><<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
-    else walk_leaf_kernel<SW, 2><<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
+static void launch_mode(pn2_ctx *h, const WalkArgs &a, int mode, cudaStream_t st, unsigned grid) {
+    if (mode == 0 && h->prm.longshort) walk_fused_kernel<SW, true><<<grid, WALK_WARPS * 32, 0, st>>>(a, h->pc);
+    else if (mode == 0) walk_fused_kernel<SW, false><<<grid, WALK_WARPS * 32, 0, st>>>(a, h->pc);
+    else if (mode == 3 && h->prm.longshort) walk_fused_f64_kernel<SW, true><<<grid, WALK_WARPS * 32, 0, st>>>(a, h->pc);
+    else if (mode == 3) walk_fused_f64_kernel<SW, false><<<grid, WALK_WARPS * 32, 0, st>>>(a, h->pc);
+    else if (mode == 1) walk_leaf_kernel<SW, 1><<<grid, WALK_WARPS * 32, 0, st>>>(a, h->pc);
+    else walk_leaf_kernel<SW, 2><<<grid, WALK_WARPS * 32, 0, st>>>(a, h->pc);
     h->launches++;
+}
+// the leaf kernel of `mode` over a's item range on stream st; grid = 0: one warp per item of [item_lo, item_hi)
+static void launch_leaves(pn2_ctx *h, const WalkArgs &a, int mode, cudaStream_t st, unsigned grid) {
+    if (grid == 0) {
+        const int items = a.item_hi - a.item_lo;
+        if (items <= 0) return;
+        grid = (unsigned)((items + WALK_WARPS - 1) / WALK_WARPS);
+        const unsigned gcap = (unsigned)(h->sm_count > 0 ? h->sm_count : 148) * LEAF_MIN_BLOCKS * 4;
+        if (a.work_count && (mode == 0 || mode == 3) && grid > gcap) grid = gcap;      // active leaves only: a bounded grid strides over their list
+    }
+    const int ml = h->prm.maxleaf;
+    if (ml <= 8) launch_mode<8>(h, a, mode, st, grid);
+    else if (ml <= 16) launch_mode<16>(h, a, mode, st, grid);
+    else launch_mode<32>(h, a, mode, st, grid);
 }
 
 static void fill_args(pn2_ctx *h, WalkArgs &a) {
@@ -958,10 +970,41 @@ static void fill_args(pn2_ctx *h, WalkArgs &a) {
     a.m2l_t = h->m2l_pairs.p; a.m2l_s = h->m2l_pairs.p + h->m2l_cap; a.m2l_cap = h->m2l_cap;
     a.counters = h->counters.p;
     a.lst_off = h->lst_off.p; a.lst_src = h->lst_src.p;
+    a.item_lo = 0; a.item_hi = h->nleaf;
 }
 
-// Pass 1 over all levels.  counters[6] is the span bump pointer (unit 0 is reserved: 0 = "no span").
+// one frontier launch over `cnt` work items (a.work / a.nwork set by the caller); gcap > 0 bounds the grid (the kernel strides)
+static void launch_frontier(pn2_ctx *h, WalkArgs &a, int cnt, unsigned gcap) {
+    a.nwork = cnt;
+    unsigned grid = (unsigned)((cnt + WALK_WARPS - 1) / WALK_WARPS);
+    if (gcap > 0 && grid > gcap) grid = gcap;
+    frontier_node_kernel<<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
+    h->launches++;
+}
+
+// Pass 1 over the levels lev0 .. lev1 - 1.  counters[6] is the span bump pointer (unit 0 is reserved: 0 = "no span").
 // h->walk_active: the pass over the received trees -- levels and leaves are visited through active lists built on the way.
+static int walk_frontier_levels(pn2_ctx *h, WalkArgs &a, int lev0, int lev1) {
+    for (int lev = lev0; lev < lev1; lev++) {
+        int cnt = h->level_off[lev + 1] - h->level_off[lev];
+        if (cnt == 0) continue;
+        if (h->walk_active) {
+            a.work = h->act_nodes.p + h->level_off[lev];
+            a.work_count = h->act_count.p + lev;
+            a.next_work = lev + 1 < h->nlevel ? h->act_nodes.p + h->level_off[lev + 1] : h->act_nodes.p;     // the last level has no node sons
+            a.next_count = h->act_count.p + lev + 1;
+            a.leaf_work = h->act_leaf.p;
+            a.leaf_count = h->act_count.p + h->nlevel + 1;
+        } else {
+            a.work = h->level_nodes.p + h->level_off[lev];
+        }
+        // the active list of a pass over the received trees is short (cells near the domain surface): a few waves of CTAs
+        // stride over it instead of one CTA per four cells of the level, most of which would exit at once
+        launch_frontier(h, a, cnt, h->walk_active ? (unsigned)(h->sm_count > 0 ? h->sm_count : 148) * NODE_MIN_BLOCKS * 2 : 0u);
+    }
+    return PN2_OK;
+}
+
 int pn2_walk_frontiers(pn2_ctx *h) {
     if (h->nnode == 0) return PN2_OK;
     WalkArgs a;
@@ -977,44 +1020,14 @@ int pn2_walk_frontiers(pn2_ctx *h) {
         CUDA_TRY(cudaMemcpyAsync(h->act_nodes.p, &root, sizeof(int), cudaMemcpyHostToDevice, h->stream));
         CUDA_TRY(cudaMemcpyAsync(h->act_count.p, &one, sizeof(unsigned), cudaMemcpyHostToDevice, h->stream));
     }
-    for (int lev = 0; lev < h->nlevel; lev++) {
-        int cnt = h->level_off[lev + 1] - h->level_off[lev];
-        if (cnt == 0) continue;
-        if (h->walk_active) {
-            a.work = h->act_nodes.p + h->level_off[lev];
-            a.work_count = h->act_count.p + lev;
-            a.next_work = lev + 1 < h->nlevel ? h->act_nodes.p + h->level_off[lev + 1] : h->act_nodes.p;     // the last level has no node sons
-            a.next_count = h->act_count.p + lev + 1;
-            a.leaf_work = h->act_leaf.p;
-            a.leaf_count = h->act_count.p + h->nlevel + 1;
-        } else {
-            a.work = h->level_nodes.p + h->level_off[lev];
-        }
-        a.nwork = cnt;
-        unsigned grid = (unsigned)((cnt + WALK_WARPS - 1) / WALK_WARPS);
-        // the active list of a pass over the received trees is short (cells near the domain surface): a few waves of CTAs
-        // stride over it instead of one CTA per four cells of the level, most of which would exit at once
-        const unsigned gcap = (unsigned)(h->sm_count > 0 ? h->sm_count : 148) * NODE_MIN_BLOCKS * 2;
-        if (h->walk_active && grid > gcap) grid = gcap;
-        frontier_node_kernel<<<grid, WALK_WARPS * 32, 0, h->stream>>>(a, h->pc);
-        h->launches++;
-    }
+    PN2_TRY(walk_frontier_levels(h, a, 0, h->nlevel));
     KERNEL_CHECK();
     return PN2_OK;
 }
 
-// dump = 0: the product step (P2P evaluated, leaf-level M2L pairs appended);
-// dump = 1 / 2: list dump passes (count / fill) for pn2_get_lists
-int pn2_walk_fused(pn2_ctx *h, int dump) {
-    if (h->nleaf == 0) return PN2_OK;
-    WalkArgs a;
-    fill_args(h, a);
-    a.pass = dump == 2 ? 1 : 0;
-    a.emit_m2l = dump == 0;
-    if (h->walk_active && dump == 0) { a.work = h->act_leaf.p; a.work_count = h->act_count.p + h->nlevel + 1; }
-    // PN2_FP64: table-driven FP64 kernel (3); PN2_FP64_LIBM: the reference's expression with libm (1); PN2_FP32: 0
-    int mode = dump ? 2 : (h->prm.precision == PN2_FP64 ? 3 : (h->prm.precision == PN2_FP64_LIBM ? 1 : 0));
-    int ml = h->prm.maxleaf;
+// leaf tiles of the leaf kernel of `mode` (FP32: 0, FP64 tables: 3), built on the context's stream; sets a.tiles / tiles64 / pad_tile
+static int prepare_tiles(pn2_ctx *h, WalkArgs &a, int mode) {
+    const int ml = h->prm.maxleaf;
     if (mode == 3) {
         const int sw = ml <= 8 ? 8 : (ml <= 16 ? 16 : 32);
         const int nt = h->nleaf + h->nrl;
@@ -1055,9 +1068,26 @@ int pn2_walk_fused(pn2_ctx *h, int dump) {
         h->tiles_built_for = h->step_serial;
         a.tiles = h->tiles.p; a.pad_tile = nt;
     }
-    if (ml <= 8) launch_mode<8>(h, a, mode);
-    else if (ml <= 16) launch_mode<16>(h, a, mode);
-    else launch_mode<32>(h, a, mode);
+    return PN2_OK;
+}
+
+// PN2_FP64: table-driven FP64 kernel (3); PN2_FP64_LIBM: the reference's expression with libm (1); PN2_FP32: 0; list dump: 2
+static int leaf_mode(const pn2_ctx *h, int dump) {
+    return dump ? 2 : (h->prm.precision == PN2_FP64 ? 3 : (h->prm.precision == PN2_FP64_LIBM ? 1 : 0));
+}
+
+// dump = 0: the product step (P2P evaluated, leaf-level M2L pairs appended);
+// dump = 1 / 2: list dump passes (count / fill) for pn2_get_lists
+int pn2_walk_fused(pn2_ctx *h, int dump) {
+    if (h->nleaf == 0) return PN2_OK;
+    WalkArgs a;
+    fill_args(h, a);
+    a.pass = dump == 2 ? 1 : 0;
+    a.emit_m2l = dump == 0;
+    if (h->walk_active && dump == 0) { a.work = h->act_leaf.p; a.work_count = h->act_count.p + h->nlevel + 1; }
+    const int mode = leaf_mode(h, dump);
+    PN2_TRY(prepare_tiles(h, a, mode));
+    launch_leaves(h, a, mode, h->stream, 0);
     KERNEL_CHECK();
     return PN2_OK;
 }

@@ -11,7 +11,7 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpn2gpu.so")
+LIB_PATH = os.environ.get("PN2GPU_LIB") or os.path.join(HERE, "libpn2gpu.so")      # PN2GPU_LIB: a kernel-parameter variant of the library (tools/build_variants.sh)
 NM = 20
 FP64, FP32, FP64_LIBM = 0, 1, 2       # include/pn2gpu.h: PN2_FP64 (table-driven, no libm), PN2_FP32, PN2_FP64_LIBM (checker)
 

@@ -85,3 +85,4 @@ def test_idempotent(pn2, workload):
     ctx, a1 = run(pn2, pos, box, mass, pn2.FP32)
     a2 = ctx.force_step(pos)
     assert np.array_equal(a1, a2)
+
