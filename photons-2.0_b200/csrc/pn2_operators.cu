@@ -158,9 +158,20 @@ __global__ void __launch_bounds__(OP_WARPS * 32) m2l_warp_kernel(long nseg, cons
                                                                  double *__restrict__ L, P2PConst pc, unsigned char *__restrict__ has_l) {
     constexpr int SPW = 32 / LPS;                          // sinks per warp
     __shared__ double s_tile[OP_WARPS][32 * REC_STRIDE];
+    __shared__ double s_tabE[PN2_M2LTAB_DEG + 1][PN2_M2LTAB_KPAD], s_tabX[PN2_M2LTAB_DEG + 1][PN2_M2LTAB_KPAD];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int g = lane / LPS, gl = lane % LPS;
-    const long k = ((long)blockIdx.x * OP_WARPS + wib) * SPW + g;
+    if (pc.longshort) {                                    // the tables of erfc(u) and exp(-u^2)/sqrt(pi), once per CTA (the grid strides)
+        for (int i = threadIdx.x; i < (PN2_M2LTAB_DEG + 1) * PN2_M2LTAB_KPAD; i += blockDim.x) {
+            (&s_tabE[0][0])[i] = (&PN2_M2LTAB_E[0][0])[i];
+            (&s_tabX[0][0])[i] = (&PN2_M2LTAB_X[0][0])[i];
+        }
+        __syncthreads();
+    }
+    const pn2op::M2LTab tab = {s_tabE, s_tabX};
+    const long ngroup = (nseg + SPW - 1) / SPW;            // one warp per group of SPW sinks
+    for (long grp = (long)blockIdx.x * OP_WARPS + wib; grp < ngroup; grp += (long)gridDim.x * OP_WARPS) {
+    const long k = grp * SPW + g;
     const bool on = k < nseg;
     int t = 0;
     long o0 = 0, o1 = 0;
@@ -190,7 +201,7 @@ __global__ void __launch_bounds__(OP_WARPS * 32) m2l_warp_kernel(long nseg, cons
             const double sx = src_geom[6 * (size_t)sc] + pc.shift[img][0];
             const double sy = src_geom[6 * (size_t)sc + 1] + pc.shift[img][1];
             const double sz = src_geom[6 * (size_t)sc + 2] + pc.shift[img][2];
-            m2l_add(cx - sx, cy - sy, cz - sz, m, l, pc.rs, pc.longshort);
+            m2l_add(cx - sx, cy - sy, cz - sz, m, l, pc.rs, pc.longshort, &tab, pc.inv2rs);
         }
     }
     double mine = 0.0;                                     // lane gl < 20 of the group ends up with component gl
@@ -204,6 +215,8 @@ __global__ void __launch_bounds__(OP_WARPS * 32) m2l_warp_kernel(long nseg, cons
     }
     if (on && gl < (LPS >= NM ? NM : LPS)) L[(size_t)t * NM + gl] = had ? L[(size_t)t * NM + gl] + mine : mine;
     if (on && gl == 0 && has_l) has_l[t] = 1;
+    __syncwarp();
+    }   // sink groups of this warp
 }
 
 static inline int nblk(long n, int b) { return (int)((n + b - 1) / b); }
@@ -250,12 +263,17 @@ int pn2_launch_m2l(pn2_ctx *h, const CsrList &list, const double *src_geom, cons
     unsigned char *flags = h->use_lflags ? h->has_l.p : nullptr;
     // a warp per sink when the lists are long (clustered / NSIDE < particle side), 8 lanes per sink otherwise
     const long npair = list.npair > 0 ? list.npair : 32 * list.nseg;
-    if (npair >= 24 * list.nseg)
-        m2l_warp_kernel<32><<<nblk(list.nseg, OP_WARPS), OP_WARPS * 32, 0, h->stream>>>(list.nseg, list.seg_sink, list.seg_off, list.src,
+    // the grid strides over the sink groups (the tables of the split functions are loaded once per CTA): at most 16 waves of CTAs
+    const int gmax = (h->sm_count > 0 ? h->sm_count : 148) * 4 * 16;
+    if (npair >= 24 * list.nseg) {
+        const int grid = nblk(list.nseg, OP_WARPS);
+        m2l_warp_kernel<32><<<grid < gmax ? grid : gmax, OP_WARPS * 32, 0, h->stream>>>(list.nseg, list.seg_sink, list.seg_off, list.src,
                                                                                       h->geom.p, src_geom, src_M, h->L.p, h->pc, flags);
-    else
-        m2l_warp_kernel<8><<<nblk(list.nseg, OP_WARPS * 4), OP_WARPS * 32, 0, h->stream>>>(list.nseg, list.seg_sink, list.seg_off, list.src,
-                                                                                         h->geom.p, src_geom, src_M, h->L.p, h->pc, flags);
+    } else {
+        const int grid = nblk(list.nseg, OP_WARPS * 4);
+        m2l_warp_kernel<8><<<grid < gmax ? grid : gmax, OP_WARPS * 32, 0, h->stream>>>(list.nseg, list.seg_sink, list.seg_off, list.src,
+                                                                                     h->geom.p, src_geom, src_M, h->L.p, h->pc, flags);
+    }
     h->launches++;
     KERNEL_CHECK();
     return PN2_OK;

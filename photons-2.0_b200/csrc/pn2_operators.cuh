@@ -8,6 +8,8 @@
 //     idx = {0,1,4,10}[o] + t(t+1)/2 + c
 #pragma once
 #include "pn2_common.cuh"
+#define PN2_M2LTAB_QUAL static __device__
+#include "pn2_m2ltab.h"
 
 namespace pn2op {
 
@@ -96,12 +98,50 @@ __device__ __forceinline__ void l2p_eval(double dx, double dy, double dz, const 
 //   f_k = ((1/r) d/dr)^k G(r);  G = erfc(r/2rs)/r with LONGSHORT (:294-307), 1/r otherwise (:288-292)
 //   D_0 = f0, D_i = f1 R_i, D_ij = f2 R_i R_j + f1 delta_ij,
 //   D_ijk = f3 R_i R_j R_k + f2 (delta_ij R_k + delta_ik R_j + delta_jk R_i)
+// E(u) = erfc(u) and X(u) = exp(-u^2)/sqrt(pi) from the piecewise degree-10 tables of pn2_m2ltab.h (tools/fit_m2l64.py:
+// |error| <= 2e-16, i.e. the last bit of double; u >= 6.4: exactly 0), the tables in shared memory
+struct M2LTab {
+    const double (*E)[PN2_M2LTAB_KPAD];
+    const double (*X)[PN2_M2LTAB_KPAD];
+};
+__device__ __forceinline__ void m2l_tab_eval(const M2LTab &tab, double u, double &E, double &X) {
+    const double t = fma(u, PN2_M2LTAB_INVH, -0.5);
+    const double tm = t + 6755399441055744.0;              // round to nearest by the 2^52 + 2^51 trick (no F2I / I2F)
+    const int k = __double2loint(tm);
+    const double d = t - (tm - 6755399441055744.0);
+    const int kc = k < PN2_M2LTAB_K - 1 ? k : PN2_M2LTAB_K - 1;
+    double e = tab.E[PN2_M2LTAB_DEG][kc], x = tab.X[PN2_M2LTAB_DEG][kc];
+#pragma unroll
+    for (int j = PN2_M2LTAB_DEG - 1; j >= 0; j--) { e = fma(e, d, tab.E[j][kc]); x = fma(x, d, tab.X[j][kc]); }
+    E = e; X = x;
+}
+
+// tab != nullptr (long/short build): no libm, no division, no square root: 1/r from MUFU.RSQ64H + two Newton steps
 __device__ __forceinline__ void m2l_add(double Rx, double Ry, double Rz, const double M[NM], double L[NM], double rs,
-                                        int longshort) {
+                                        int longshort, const M2LTab *tab = nullptr, double inv2rs = 0.0) {
     double r2 = Rx * Rx + Ry * Ry + Rz * Rz;
+    double f0, f1, f2, f3;
+    if (longshort && tab) {
+        double y;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(r2));
+        double e = fma(-(r2 * y), y, 1.0);
+        y = fma(0.5 * y, e, y);                             // ~1e-12
+        e = fma(-(r2 * y), y, 1.0);
+        const double ir = fma(0.5 * y, e, y);               // 1/r to the last bits
+        const double ir2 = ir * ir, r = r2 * ir;
+        const double irs = 2.0 * inv2rs;                    // 1 / rs
+        double E, X;
+        m2l_tab_eval(*tab, r * inv2rs, E, X);
+        const double irs2 = irs * irs;
+        const double a = X * irs;                           // X / rs
+        const double b = E * ir + a;
+        f0 = E * ir;
+        f1 = -b * ir2;
+        f2 = (3.0 * b * ir2 + 0.5 * a * irs2) * ir2;
+        f3 = -((15.0 * b * ir2 + 2.5 * a * irs2) * ir2 + 0.25 * a * irs2 * irs2) * ir2;
+    } else {
     double r = sqrt(r2);
     double ir = 1.0 / r, ir2 = ir * ir;
-    double f0, f1, f2, f3;
     if (longshort) {
         double irs = 1.0 / rs;
         double u = 0.5 * r * irs;
@@ -115,6 +155,7 @@ __device__ __forceinline__ void m2l_add(double Rx, double Ry, double Rz, const d
         f3 = -((15.0 * (E * ir + a) * ir2 + 2.5 * a * irs2) * ir2 + 0.25 * a * irs2 * irs2) * ir2;
     } else {
         f0 = ir; f1 = -ir * ir2; f2 = 3.0 * ir * ir2 * ir2; f3 = -15.0 * ir * ir2 * ir2 * ir2;
+    }
     }
     double R[3] = {Rx, Ry, Rz};
     double D[NM];

@@ -13,8 +13,8 @@
 // with __shfl_xor at the end, so every sink is owned by one warp: no atomics, deterministic sums.
 //
 // FP32 mode: coordinates are leaf-centre-relative and in units of lambda = 2 rs sqrt(ln 2) (see below):
-//     3 FADD (dx) + 3 FFMA (r^2) + MUFU.RSQ + FMUL (u) + MUFU.EX2 (2^(-r^2)) + 9 FFMA (1 + u^2 R(u))
-//     + FMNMX (softening) + 2 FMUL (1/r^3) + 2 FMUL (e, Q) + 3 FFMA (accumulate)  = 23 FMA-pipe + 2 MUFU + 1 ALU
+//     3 FADD (dx) + 3 FFMA (r^2) + MUFU.RSQ + FMUL (u) + MUFU.EX2 (2^(-r^2)) + 8 FFMA (1 + u^2 R(u), deg R = 7)
+//     + FMNMX (softening) + 2 FMUL (1/r^3) + 2 FMUL (e, Q) + 3 FFMA (accumulate)  = 22 FMA-pipe + 2 MUFU + 1 ALU
 #pragma once
 #include "pn2_common.cuh"
 
@@ -23,14 +23,16 @@
 // register operand costs FMA-pipe cycles (measured, tools/ubench/ubench_ops.cu: FFMA2 with two register pairs +
 // immediate 2.04 cycles, + scalar register 2.21, three pairs 3.03).
 #ifndef PN2_RDEG
-#define PN2_RDEG 8                // deg R = 8: |err g| <= 3.3e-7;  6: <= 3.3e-6
+#define PN2_RDEG 7                // deg R = 8: |err g| <= 3.3e-7;  7: <= 8.9e-7 (the default);  6: <= 3.3e-6
 #endif
 #if PN2_RDEG == 8
 #define PN2_RCOEF {9.998987644e-01f, -7.508830079e-01f, 4.927910981e-01f, -2.807554342e-01f, 1.325016193e-01f, -4.790751029e-02f, 1.200598312e-02f, -1.810827398e-03f, 1.218777145e-04f}
+#elif PN2_RDEG == 7
+#define PN2_RCOEF {9.996877624e-01f, -7.485814399e-01f, 4.833320565e-01f, -2.610572656e-01f, 1.093096686e-01f, -3.186952180e-02f, 5.574667193e-03f, -4.318225181e-04f}
 #elif PN2_RDEG == 6
 #define PN2_RCOEF {9.990517726e-01f, -7.427107543e-01f, 4.632659763e-01f, -2.271847688e-01f, 7.821331668e-02f, -1.612388462e-02f, 1.459452176e-03f}
 #else
-#error "PN2_RDEG must be 6 or 8"
+#error "PN2_RDEG must be 6, 7 or 8"
 #endif
 // FP32 length unit: lambda = 2 rs sqrt(ln 2), so that exp(-u^2) = 2^(-r'^2) with r' = r / lambda and MUFU.EX2 takes
 // -r'^2 directly (saves the multiplication by log2 e per interaction).  The polynomial is rescaled accordingly at
@@ -125,8 +127,8 @@ __device__ __forceinline__ void p2p_interact_f32(const float4 pj, float xi, floa
 }
 
 // Packed form: one sink lane against TWO staged sources.  Same operations as p2p_interact_f32, each FMA-pipe
-// instruction doing both sources: 3 FADD2 + 3 FFMA2 + 2 FMUL2 (1/r^3) + FMUL2 (u) + 9 FFMA2
-// + 2 FMUL2 + 3 FFMA2 = 23 FMA-pipe instructions, 4 MUFU, 2 FMNMX, 2 LDS per PAIR of interactions (16 issue
+// instruction doing both sources: 3 FADD2 + 3 FFMA2 + 2 FMUL2 (1/r^3) + FMUL2 (u) + 8 FFMA2
+// + 2 FMUL2 + 3 FFMA2 = 22 FMA-pipe instructions, 4 MUFU, 2 FMNMX, 2 LDS per PAIR of interactions (15 issue
 // slots per interaction instead of 28), so the FMA pipe (2 cycles per FP32x2 instruction), not the issue port, bounds it.
 struct P2PSinkPk {
     pn2_f2 nx, ny, nz;      // (-xi, -xi) ...
