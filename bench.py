@@ -402,6 +402,16 @@ def main():
     else:
         ms_total, nint_total, n_total, walk_ms = [float(x) for x in t]
     ms_step = ms_total / args.steps
+    # per rank: step time and the rank's own phases (the job's step is the slowest rank's)
+    per_rank = None
+    if world > 1:
+        mine = torch.tensor([float(t[0]) / args.steps, float(info["n_interactions"]), float(n)] +
+                            [float(np.mean([p[k] for p in phase])) for k in ("tree", "frontier", "walk_p2p", "let")], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"ms_per_step": [float(x[0]) for x in allr], "interactions": [float(x[1]) for x in allr], "particles": [float(x[2]) for x in allr],
+                    "tree_ms": [float(x[3]) for x in allr], "frontier_ms": [float(x[4]) for x in allr], "walk_p2p_ms": [float(x[5]) for x in allr],
+                    "let_exposed_ms": [float(x[6]) for x in allr]}
     # Newton's third law over the whole periodic set: |sum a| / sum |a| (all ranks), a size-independent property check
     mom = torch.cat([acc.sum(0), torch.linalg.vector_norm(acc, dim=1).sum().reshape(1)])
     if world > 1:
@@ -522,7 +532,7 @@ def main():
            "config": workload_config(args, world),
            "p2p_ginteractions_per_s": nint_total / (ms_step * 1e-3) / 1e9,
            "interactions_per_particle": nint_total / n_total,
-           "migrate": migrate, "momentum_residual": momentum_residual, "rebalance": rebalance, "pm_long_range": pm,
+           "migrate": migrate, "momentum_residual": momentum_residual, "rebalance": rebalance, "pm_long_range": pm, "per_rank": per_rank,
            "phases_ms": {k: float(np.mean([p[k] for p in phase])) for k in ("tree", "upward", "frontier", "walk_p2p", "m2l", "m2l_kernel", "downward", "let", "total")},
            "tree": {"nleaf": info["nleaf"], "nnode": info["nnode"], "levels": info["nlevel"], "m2l_pairs": info["n_m2l_pairs"],
                     "p2p_leaf_pairs": info["n_p2p_pairs"], "walk_visits": info["n_walk_visits"],

@@ -142,6 +142,8 @@ struct pn2_ctx {
     DBuf<double> n_box, n_split, l_box;                              // [cap][6] lo, hi
     DBuf<unsigned long long> b_cnt;  // per-level child counts (leaf | node << 32) and scan
     DBuf<int> b_scal;                // device scalars
+    DBuf<int> b_lv;                  // per-level {node count, first node, leaves so far, -} of the deferred tree levels
+    int tree_levels_hint = 0;        // levels of the previous step's tree: where the builder starts reading the counts back
     DBuf<unsigned> spans;            // O(im) span lists of the frontier pass (16-byte units)
     unsigned long long span_cap16 = 0, span_used16 = 0, walk_visits = 0;
     DBuf<unsigned> o_head;           // [ncell]

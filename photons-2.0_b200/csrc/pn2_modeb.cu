@@ -11,7 +11,7 @@ void pn2_modeb_release(pn2_ctx *h) {
     h->b_seg.release(); h->b_seg2.release(); h->b_q.release(); h->b_key2.release(); h->b_f.release(); h->b_flag.release();
     h->n_start.release(); h->n_count.release(); h->n_son.release(); h->n_depth.release(); h->l_start.release();
     h->l_count.release(); h->n_box.release(); h->n_split.release(); h->l_box.release(); h->b_cnt.release();
-    h->b_scal.release(); h->act_nodes.release(); h->act_leaf.release(); h->act_count.release(); h->stage_in.release(); h->stage_out.release(); h->m2l_pairs.release(); h->spans.release(); h->o_head.release(); h->lst_off.release(); h->lst_src.release(); h->lst_sink.release();
+    h->b_scal.release(); h->b_lv.release(); h->act_nodes.release(); h->act_leaf.release(); h->act_count.release(); h->stage_in.release(); h->stage_out.release(); h->m2l_pairs.release(); h->spans.release(); h->o_head.release(); h->lst_off.release(); h->lst_src.release(); h->lst_sink.release();
     for (int i = 0; i < PN2_NEV; i++) if (h->ev[i]) { cudaEventDestroy(h->ev[i]); h->ev[i] = nullptr; }
     pn2_let_release(h);
     pn2_migrate_release(h);

@@ -182,6 +182,18 @@ __global__ void split_kernel(int cnt, int node0, const int *__restrict__ n_count
     n_split[nd] = __dadd_rn(lo, __dmul_rn(m, invS));
 }
 
+// Deferred levels: the level's {node count, first node, leaves so far} live in DEVICE memory (lv[0..2], written by the
+// previous level's children_top_kernel), so that the host can enqueue several levels without waiting for the counts:
+// grids are sized by an upper bound (twice the previous level's) and threads beyond the count exit.
+__global__ void split_top_kernel(const int *__restrict__ lv, const int *__restrict__ n_count, const unsigned long long *__restrict__ n_sum,
+                                 double lo, double invS, double *__restrict__ n_split) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= lv[0]) return;
+    int nd = lv[1] + k;
+    double m = __ddiv_rn(__ull2double_rn(n_sum[nd]), (double)n_count[nd]);
+    n_split[nd] = __dadd_rn(lo, __dmul_rn(m, invS));
+}
+
 // per node: how many leaf / node children (packed leaf | node << 32) for the numbering scan
 __global__ void childcount_kernel(int cnt, int node0, const int *__restrict__ n_start, const int *__restrict__ n_count,
                                   const int *__restrict__ F, int maxleaf, unsigned long long *__restrict__ cc) {
@@ -286,9 +298,11 @@ __global__ void scatter_kernel(int n, const uint4 *__restrict__ pay, const int *
 __device__ __forceinline__ unsigned pay_dir(const uint4 &p, int dir) { return dir == 0 ? p.x : (dir == 1 ? p.y : p.z); }
 
 __global__ void __launch_bounds__(TB) top_level_kernel(int n, const unsigned *__restrict__ qd, const unsigned *__restrict__ qn,
-                                                       int *__restrict__ seg, const int *__restrict__ slot2id, int node0,
+                                                       int *__restrict__ seg, const int *__restrict__ slot2id, const int *__restrict__ lv,
                                                        const int *__restrict__ n_count, const unsigned long long *__restrict__ n_sum,
                                                        unsigned long long *__restrict__ csum, unsigned *__restrict__ ccnt) {
+    if (lv[0] == 0) return;                 // a level enqueued past the end of the tree: nothing to relabel
+    const int node0 = lv[1];
     __shared__ int t_key[TOP_TAB];
     __shared__ unsigned long long t_sum[TOP_TAB];
     __shared__ unsigned t_cnt[TOP_TAB];
@@ -369,9 +383,11 @@ __global__ void __launch_bounds__(TB) top_level_kernel(int n, const unsigned *__
         }
 }
 
-__global__ void childcount_top_kernel(int cnt, const unsigned *__restrict__ ccnt, int maxleaf, unsigned long long *__restrict__ cc) {
+__global__ void childcount_top_kernel(const int *__restrict__ lv, int bound, const unsigned *__restrict__ ccnt, int maxleaf,
+                                      unsigned long long *__restrict__ cc) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k > cnt) return;
+    if (k > bound) return;                  // the scan runs over bound + 1 entries: zeros beyond the level's count
+    const int cnt = lv[0];
     unsigned long long v = 0;
     if (k < cnt) {
         unsigned nl = ((int)ccnt[2 * k] <= maxleaf) + ((int)ccnt[2 * k + 1] <= maxleaf);
@@ -382,7 +398,7 @@ __global__ void childcount_top_kernel(int cnt, const unsigned *__restrict__ ccnt
 
 // children_kernel for a deferred level: the counts come from ccnt, a node child starts with its coordinate sum, and
 // slot2id tells the next level (and the final sort) where every slot went
-__global__ void children_top_kernel(int cnt, int node0, int next_node0, int leaf0, int dir, int depth, int maxleaf,
+__global__ void children_top_kernel(const int *__restrict__ lv, int *__restrict__ lv_next, int dir, int depth, int maxleaf,
                                     int *__restrict__ n_start, int *__restrict__ n_count, int *__restrict__ n_son,
                                     int *__restrict__ n_depth, double *__restrict__ n_box, const double *__restrict__ n_split,
                                     int *__restrict__ l_start, int *__restrict__ l_count, double *__restrict__ l_box,
@@ -390,6 +406,8 @@ __global__ void children_top_kernel(int cnt, int node0, int next_node0, int leaf
                                     const unsigned long long *__restrict__ ccs, int node_cap, int leaf_cap, int *__restrict__ scal,
                                     unsigned long long *__restrict__ n_sum, int *__restrict__ slot2id) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int cnt = lv[0], node0 = lv[1], leaf0 = lv[2], next_node0 = node0 + cnt;
+    if (cnt == 0 && k == 0) { lv_next[0] = 0; lv_next[1] = node0; lv_next[2] = leaf0; }
     if (k >= cnt) return;
     int nd = node0 + k;
     int a = n_start[nd];
@@ -428,8 +446,9 @@ __global__ void children_top_kernel(int cnt, int node0, int next_node0, int leaf
     }
     if (k == cnt - 1) {
         unsigned long long tot = ccs[cnt];
-        scal[0] = (int)(tot >> 32);
-        scal[1] = leaf0 + (int)(tot & 0xffffffffULL);
+        lv_next[0] = (int)(tot >> 32);                            // nodes of the next level
+        lv_next[1] = next_node0;
+        lv_next[2] = leaf0 + (int)(tot & 0xffffffffULL);          // leaves so far
     }
 }
 
@@ -602,33 +621,52 @@ static int tree_build_once(pn2_ctx *h, const double *d_pos_in, int n, const pn2_
         h->launches++;
         unsigned long long *csum = h->b_key2.p;
         unsigned *ccnt = reinterpret_cast<unsigned *>(h->b_f.p);
-        int *s2i_prev = nullptr, *s2i = h->b_idx2.p, *s2i_other = h->b_seg2.p;
-        while (cnt > 0) {
+        int *s2i_buf[2] = {h->b_idx2.p, h->b_seg2.p};               // slot table of level l: s2i_buf[l & 1]
+        // level descriptors {count, first node, leaves so far, -} in device memory: the levels are enqueued back to back
+        // with grids sized by an upper bound of the count (it at most doubles per level); the host reads the counts
+        // only where it has to -- every level on the first build, afterwards only over the last levels of the previous
+        // step's tree (where the counts stop doubling and the tree ends)
+        const int MAXLV = 208;
+        PN2_TRY(h->b_lv.ensure(4 * MAXLV));
+        std::vector<int> lvh(4 * MAXLV, 0);
+        lvh[0] = 1;
+        CUDA_TRY(cudaMemcpyAsync(h->b_lv.p, lvh.data(), 4 * sizeof(int), cudaMemcpyHostToDevice, st));
+        const int sync_from = h->tree_levels_hint > 0 ? h->tree_levels_hint - 4 : 0;
+        long bound = 1;
+        bool ended = false;
+        while (!ended) {
             if (level > 200) { pn2_set_error("pn2: tree deeper than 200 levels (more than MAXLEAF coincident particles?)"); return PN2_ERR_ARG; }
             const int dir = (dom->direct0 + level) % 3;
-            split_kernel<<<nb(cnt), TB, 0, st>>>(cnt, node0, h->n_count.p, h->n_sum.p, dom->lo[dir], invS, h->n_split.p);
-            CUDA_TRY(cudaMemsetAsync(csum, 0, 2 * (size_t)cnt * sizeof(unsigned long long), st));
-            CUDA_TRY(cudaMemsetAsync(ccnt, 0, 2 * (size_t)cnt * sizeof(unsigned), st));
-            top_level_kernel<<<nb(((long)n + TOP_ITEMS - 1) / TOP_ITEMS), TB, 0, st>>>(n, qsoa[dir], qsoa[(dir + 1) % 3], sg, s2i_prev, node0,
+            const int *lv = h->b_lv.p + 4 * level;
+            const int b = (int)bound;
+            split_top_kernel<<<nb(b), TB, 0, st>>>(lv, h->n_count.p, h->n_sum.p, dom->lo[dir], invS, h->n_split.p);
+            CUDA_TRY(cudaMemsetAsync(csum, 0, 2 * (size_t)b * sizeof(unsigned long long), st));
+            CUDA_TRY(cudaMemsetAsync(ccnt, 0, 2 * (size_t)b * sizeof(unsigned), st));
+            top_level_kernel<<<nb(((long)n + TOP_ITEMS - 1) / TOP_ITEMS), TB, 0, st>>>(n, qsoa[dir], qsoa[(dir + 1) % 3], sg, level > 0 ? s2i_buf[(level - 1) & 1] : nullptr, lv,
                                                                                    h->n_count.p, h->n_sum.p, csum, ccnt);
-            childcount_top_kernel<<<nb(cnt + 1), TB, 0, st>>>(cnt, ccnt, maxleaf, h->b_q.p);
-            cub::DeviceScan::ExclusiveSum(h->tmp.p, tb4, h->b_q.p, h->b_q.p, cnt + 1, st);
-            children_top_kernel<<<nb(cnt), TB, 0, st>>>(cnt, node0, node0 + cnt, nleaf, dir, level, maxleaf, h->n_start.p, h->n_count.p,
-                                                        h->n_son.p, h->n_depth.p, h->n_box.p, h->n_split.p, h->l_start.p, h->l_count.p,
-                                                        h->l_box.p, csum, ccnt, h->b_q.p, cap, cap, h->b_scal.p, h->n_sum.p, s2i);
+            childcount_top_kernel<<<nb(b + 1), TB, 0, st>>>(lv, b, ccnt, maxleaf, h->b_q.p);
+            cub::DeviceScan::ExclusiveSum(h->tmp.p, tb4, h->b_q.p, h->b_q.p, b + 1, st);
+            children_top_kernel<<<nb(b), TB, 0, st>>>(lv, h->b_lv.p + 4 * (level + 1), dir, level, maxleaf, h->n_start.p, h->n_count.p,
+                                                      h->n_son.p, h->n_depth.p, h->n_box.p, h->n_split.p, h->l_start.p, h->l_count.p,
+                                                      h->l_box.p, csum, ccnt, h->b_q.p, cap, cap, h->b_scal.p, h->n_sum.p, s2i_buf[level & 1]);
             h->launches += 5;
-            int hs[4];
-            CUDA_TRY(cudaMemcpyAsync(hs, h->b_scal.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(cudaStreamSynchronize(st));
-            if (hs[3]) { *overflow = true; return PN2_OK; }
-            s2i_prev = s2i; std::swap(s2i, s2i_other);
-            node0 += cnt;
-            level_off.push_back(node0);
-            cnt = hs[0];
-            nleaf = hs[1];
-            leaf_off.push_back(nleaf);
             level++;
+            bound = 2 * bound > (long)cap ? (long)cap : 2 * bound;
+            if (level >= sync_from) {
+                int hs[4];
+                CUDA_TRY(cudaMemcpyAsync(lvh.data(), h->b_lv.p, 4 * (size_t)(level + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaMemcpyAsync(hs, h->b_scal.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaStreamSynchronize(st));
+                if (hs[3]) { *overflow = true; return PN2_OK; }
+                for (int l = 1; l <= level && !ended; l++)
+                    if (lvh[4 * l] == 0) { level = l; ended = true; }          // level l has no nodes: the tree has l levels (levels enqueued past it did nothing)
+                if (!ended) bound = lvh[4 * level];
+            }
         }
+        for (int l = 1; l <= level; l++) { level_off.push_back(lvh[4 * l + 1]); leaf_off.push_back(lvh[4 * l + 2]); }
+        node0 = lvh[4 * level + 1]; nleaf = lvh[4 * level + 2]; cnt = 0;
+        h->tree_levels_hint = level;
+        int *s2i_prev = s2i_buf[(level - 1) & 1], *s2i = s2i_buf[level & 1];
         // tree order: sort the Morton ranks by the start position of their leaf (stable), then fetch positions / caller indices
         unsigned *key = h->b_qc.p, *key_s = h->b_qc2.p;
         int *iota = s2i, *vals = reinterpret_cast<int *>(h->b_pay2.p);      // the caller-order payload is consumed
