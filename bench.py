@@ -542,8 +542,8 @@ def main():
                         "unit": "Tops/s (FFMA/FMUL/FADD issue slots)" if fp32 else "Tops/s (DFMA/DMUL/DADD issue slots)", "frac": ach / fma_peak,
                         "peak_source": "measured in this run: pn2_fma_peak (independent %s chains, CUDA events)" % ("FFMA" if fp32 else "DFMA"),
                         "nominal_peak_at_sampled_clock": (nominal / 1e12) if nominal else None,
-                        "ops_per_interaction": OPS_PER_INTERACTION, "ops_executed_per_interaction": 22 if fp32 else 30,
-                        "frac_executed": (22 if fp32 else 30) / OPS_PER_INTERACTION * ach / fma_peak, "traffic": traffic,
+                        "ops_per_interaction": OPS_PER_INTERACTION, "ops_executed_per_interaction": 22 if fp32 else 28,
+                        "frac_executed": (22 if fp32 else 28) / OPS_PER_INTERACTION * ach / fma_peak, "traffic": traffic,
                         "hbm_peak_gbs_measured": peaks.get("hbm_gbs")},
            "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e}
     # padded tiles: the kernel evaluates SW x SW lane products per leaf pair whatever the leaves hold

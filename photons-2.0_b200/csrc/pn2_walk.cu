@@ -668,8 +668,9 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, LEAF_MIN_BLOCKS) walk_fused_k
 // Tiles: SW slots of {x, y, z, w} doubles (32 bytes), leaf-centre-relative in units of 2 rs (so u = r), w = 1, padding
 // slots far away with w = 0.  Arithmetic per interaction (reference: src/fmm.c:834-852, sqrt + division + erfc + exp
 // from libm): 3 DADD + 3 DFMA (r^2) + MUFU.RSQ64H and one Newton step (4 ops, relative error < 1e-12) + 1 DSETP
-// (softening) + 2 DMUL (1/r^3) + DMUL (u) + 2 ops and F2I / I2F (interval of the g(u) table) + 8 DFMA (degree-8
-// piece of g, |error| < 7e-11: pn2_gtab.h, tools/fit_g64.py) + DMUL + 3 DFMA = 28 FP64-pipe operations.
+// (softening) + 2 DMUL (1/r^3) + DMUL (u) + 4 ops for the interval of the g(u) table (2^52 + 2^51 rounding: no F2I / I2F)
+// + 6 DFMA (degree-6 piece of g on 31 intervals, |error| < 1.9e-10: pn2_gtab.h, tools/fit_g64.py) + DMUL + 3 DFMA
+// = 28 FP64-pipe operations.
 #include "pn2_gtab.h"
 #ifndef F64_MIN_BLOCKS
 #define F64_MIN_BLOCKS 4

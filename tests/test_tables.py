@@ -45,7 +45,7 @@ def test_fp64_p2p_table():
     assert C.shape == (deg + 1, K)
     u = np.linspace(0.0, 7.5, 200001)
     err = np.abs(eval_table(C, defs["PN2_GTAB_INVH"], K - 1, u) - np.where(u < 6.0, g_exact(u), 0.0))
-    assert err.max() < 1e-10, err.max()                     # header: 6.6e-11; north_star's FP64 tolerance is 1e-6 on accelerations
+    assert err.max() < 2e-10, err.max()                     # header: 1.9e-10; north_star's FP64 tolerance is 1e-6 on accelerations
     assert np.all(eval_table(C, defs["PN2_GTAB_INVH"], K - 1, np.array([6.01, 50.0, 1e4])) == 0.0)     # padding slots (at 1e4) / far pairs: exactly 0
 
 
