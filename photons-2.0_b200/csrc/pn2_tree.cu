@@ -652,7 +652,9 @@ static int tree_build_once(pn2_ctx *h, const double *d_pos_in, int n, const pn2_
             h->launches += 5;
             level++;
             bound = 2 * bound > (long)cap ? (long)cap : 2 * bound;
-            if (level >= sync_from) {
+            // (an unread level costs launches over `bound` nodes: past n / 16 nodes per level -- leaves are near -- the
+            //  counts of an unbalanced tree fall far below the doubling bound, so there the host reads every level again)
+            if (level >= sync_from || 2 * bound > (long)n / 16 + 1024) {
                 int hs[4];
                 CUDA_TRY(cudaMemcpyAsync(lvh.data(), h->b_lv.p, 4 * (size_t)(level + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
                 CUDA_TRY(cudaMemcpyAsync(hs, h->b_scal.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
