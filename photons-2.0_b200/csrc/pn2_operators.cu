@@ -261,19 +261,23 @@ int pn2_launch_l2l_l2p(pn2_ctx *h) {
 int pn2_launch_m2l(pn2_ctx *h, const CsrList &list, const double *src_geom, const double *src_M) {
     if (list.nseg == 0) return PN2_OK;
     unsigned char *flags = h->use_lflags ? h->has_l.p : nullptr;
-    // a warp per sink when the lists are long (clustered / NSIDE < particle side), 8 lanes per sink otherwise
     const long npair = list.npair > 0 ? list.npair : 32 * list.nseg;
     // the grid strides over the sink groups (the tables of the split functions are loaded once per CTA): at most 16 waves of CTAs
     const int gmax = (h->sm_count > 0 ? h->sm_count : 148) * 4 * 16;
-    if (npair >= 24 * list.nseg) {
-        const int grid = nblk(list.nseg, OP_WARPS);
-        m2l_warp_kernel<32><<<grid < gmax ? grid : gmax, OP_WARPS * 32, 0, h->stream>>>(list.nseg, list.seg_sink, list.seg_off, list.src,
-                                                                                      h->geom.p, src_geom, src_M, h->L.p, h->pc, flags);
-    } else {
-        const int grid = nblk(list.nseg, OP_WARPS * 4);
-        m2l_warp_kernel<8><<<grid < gmax ? grid : gmax, OP_WARPS * 32, 0, h->stream>>>(list.nseg, list.seg_sink, list.seg_off, list.src,
-                                                                                     h->geom.p, src_geom, src_M, h->L.p, h->pc, flags);
-    }
+    // lanes per sink by the mean list length: a warp per sink for long lists (clustered sets, NSIDE << particle side), 8 or 2
+    // lanes for shorter ones, so that the per-sink work (20 accumulators cleared, reduced over the sink's lanes and stored) is
+    // shared by 4 / 16 sinks per warp and fewer lanes idle behind the end of a short list (PN2_M2L_LPS = 2, 4, 8, 32 forces a width)
+    // (measured at 256^3 / NSIDE 128, 6 <= mean length < 24: 0.97 ms with 2 lanes, 0.98 with 4, 1.08 with 8)
+    int lps = npair >= 24 * list.nseg ? 32 : (npair >= 16 * list.nseg ? 8 : 2);
+    if (const char *e = getenv("PN2_M2L_LPS")) { const int v = atoi(e); if (v == 2 || v == 4 || v == 8 || v == 32) lps = v; }
+#define PN2_M2L_LAUNCH(W) do { const int grid = nblk(list.nseg, OP_WARPS * (32 / W)); \
+        m2l_warp_kernel<W><<<grid < gmax ? grid : gmax, OP_WARPS * 32, 0, h->stream>>>(list.nseg, list.seg_sink, list.seg_off, list.src, \
+                                                                                     h->geom.p, src_geom, src_M, h->L.p, h->pc, flags); } while (0)
+    if (lps == 32) PN2_M2L_LAUNCH(32);
+    else if (lps == 8) PN2_M2L_LAUNCH(8);
+    else if (lps == 4) PN2_M2L_LAUNCH(4);
+    else PN2_M2L_LAUNCH(2);
+#undef PN2_M2L_LAUNCH
     h->launches++;
     KERNEL_CHECK();
     return PN2_OK;
