@@ -47,3 +47,17 @@ def test_gpu_arm_line_small():
     assert p["pass"] and p["fp64_rms"] <= 1e-6 and p["fp32_rms"] <= 1e-4 and p["nleaf_equal"] and p["nint_equal"], p
     assert d["momentum_residual"] < 1e-6
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_fmm")), reason="oracle/_ref not built")
+def test_reference_arm_rank_count_guard(monkeypatch):
+    """The unmodified reference does not return when a domain is thinner than twice the cut-off radius (its LET exchange
+    assumes one meeting per peer through the periodic wrap: 32^3 / NSIDE 32 at 16 ranks never ends).  The CPU arm halves
+    the rank count until src/domains.c's boxes are wide enough, and says how many ranks it really used."""
+    import importlib
+    sys.path.insert(0, ROOT)
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--cpu-sample-side", "32"])
+    bench = importlib.import_module("bench")
+    args = bench.parse()
+    r = bench.reference_cpu_run(args, 32, 16)
+    assert r["kind"] == "reference" and r["cores"] == 8 and r["n"] == 32 ** 3 and r["pps"] > 0
