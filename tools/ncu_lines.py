@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Per-source-line instruction counts of one kernel: joins the SASS page of an ncu report (instructions executed,
 stall samples per SASS instruction) with the line table of the cubin (nvdisasm -g).
-usage: tools/ncu_lines.py <report.ncu-rep> <cubin> <mangled kernel name> [top N]"""
+usage: tools/ncu_lines.py <report.ncu-rep> <cubin | object file> <mangled kernel name> [top N]
+(the object must be the build the report was taken from)"""
 import collections
 import csv
 import re
@@ -19,6 +20,13 @@ for k in range(2, len(rows)):            # several captured launches: keep the f
 hdr = rows[1]
 ie, iss, isrc = hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("Source")
 prof = [(r[isrc].strip(), int(r[ie]), int(r[iss])) for r in rows[2:] if len(r) > ie]
+if cubin.endswith(".o") or cubin.endswith(".so"):        # a host object: take the sm_100a cubin out of it first
+    import glob, os, tempfile
+    td = tempfile.mkdtemp()
+    subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(cubin)], cwd=td, capture_output=True, text=True)
+    cands = sorted(glob.glob(os.path.join(td, "*.cubin")), key=os.path.getsize)
+    assert cands, "no cubin in " + cubin
+    cubin = cands[-1]
 dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
 lines, cur, on = [], None, False
 for l in dis:
